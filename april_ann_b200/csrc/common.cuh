@@ -1,0 +1,131 @@
+// Shared declarations for the sm_100a kernels and the C-ABI layer.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/b200ann.h"
+
+#define NEAR_ZERO_F 1e-6f  // packages/basics/mathcore/c_src/cmath_overloads.h:38
+
+struct b200_ctx {
+  int device = 0;
+  int sm_count = 148;
+  int math_mode = B200_MATH_FP32;
+  cudaStream_t stream = nullptr;
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_compute = nullptr, ev_comm = nullptr;
+  uint64_t launches = 0;
+  // caching pool: size -> free blocks ; ptr -> size for live blocks
+  std::multimap<size_t, void *> free_blocks;
+  std::map<void *, size_t> live_blocks;
+  std::mutex mu;
+  // scratch for reductions / split-K etc.
+  void *scratch = nullptr;
+  size_t scratch_bytes = 0;
+  // NCCL (dlopen'ed lazily)
+  void *nccl_comm = nullptr;
+  int nranks = 1, rank = 0;
+  // tcgen05 GEMM state (tensor-map cache lives in gemm_tc.cu)
+  void *tc_state = nullptr;
+};
+
+void b200_set_error(const char *fmt, ...);
+int b200_check_cuda(cudaError_t e, const char *what, const char *file, int line);
+void *b200_scratch(b200_ctx *ctx, size_t bytes);
+
+#define CUDA_TRY(expr)                                                        \
+  do {                                                                        \
+    int _st = b200_check_cuda((expr), #expr, __FILE__, __LINE__);             \
+    if (_st) return _st;                                                      \
+  } while (0)
+
+#define LAUNCH_CHECK(ctx)                                                     \
+  do {                                                                        \
+    (ctx)->launches++;                                                        \
+    int _st = b200_check_cuda(cudaGetLastError(), "kernel launch", __FILE__, __LINE__); \
+    if (_st) return _st;                                                      \
+  } while (0)
+
+#define ARG_CHECK(cond, msg)                                                  \
+  do {                                                                        \
+    if (!(cond)) {                                                            \
+      b200_set_error("%s: bad argument: %s", __func__, msg);                  \
+      return B200_ERR_BAD_ARG;                                                \
+    }                                                                         \
+  } while (0)
+
+// ---------------------------------------------------------------- scalar functors
+// Device restatement of the reference's scalar definitions (cmath_overloads.h:717-733,
+// 969-989, 1053-1080, 1115-1124).  expf (not __expf): parity mode needs <=2 ulp.
+__device__ __forceinline__ float act_apply(int act, float x) {
+  switch (act) {
+    case B200_ACT_LOGISTIC: return 1.0f / (expf(-x) + 1.0f);
+    case B200_ACT_TANH: return 2.0f / (expf(-x) + 1.0f) - 1.0f;
+    case B200_ACT_RELU: return x > 0.0f ? x : 0.0f;
+    default: return x;
+  }
+}
+// derivative evaluated from the activation OUTPUT y (relu: y>0 <=> x>0)
+__device__ __forceinline__ float act_deriv_from_output(int act, float y) {
+  switch (act) {
+    case B200_ACT_LOGISTIC: {
+      float v = fminf(fmaxf(y, NEAR_ZERO_F), 1.0f - NEAR_ZERO_F);
+      return v * (1.0f - v);
+    }
+    case B200_ACT_TANH: {
+      float v = fminf(fmaxf(y, -1.0f + NEAR_ZERO_F), 1.0f - NEAR_ZERO_F);
+      return 0.5f * (1.0f - v * v);
+    }
+    case B200_ACT_RELU: return y > 0.0f ? 1.0f : 0.0f;
+    default: return 1.0f;
+  }
+}
+
+// Epilogue shared by the FFMA and the tcgen05 contractions:
+//   v = alpha*acc ; v += bias[n] ; v = act(v) ; v *= act'(dsrc[m,n]) ; v += beta*C[m,n]
+struct GemmEpilogue {
+  float alpha = 1.0f, beta = 0.0f;
+  const float *bias = nullptr;
+  int act = B200_ACT_NONE;
+  int dact = B200_ACT_NONE;
+  const float *dsrc = nullptr;
+  int ld_dsrc = 0;
+};
+
+__device__ __forceinline__ float epilogue_apply(const GemmEpilogue &e, float acc, int m, int n,
+                                                float cold) {
+  float v = e.alpha * acc;
+  if (e.bias) v += __ldg(e.bias + n);
+  if (e.act != B200_ACT_NONE) v = act_apply(e.act, v);
+  if (e.dact != B200_ACT_NONE) v *= act_deriv_from_output(e.dact, __ldg(e.dsrc + (size_t)m * e.ld_dsrc + n));
+  if (e.beta != 0.0f) v += e.beta * cold;
+  return v;
+}
+
+// internal entry points shared between translation units
+int gemm_simt(b200_ctx *ctx, int transA, int transB, int M, int N, int K, const float *A, int lda,
+              const float *B, int ldb, float *C, int ldc, const GemmEpilogue &ep);
+// returns B200_ERR_UNSUPPORTED when the shape/alignment cannot use the tensor path
+int gemm_tc(b200_ctx *ctx, int transA, int transB, int M, int N, int K, const float *A, int lda,
+            const float *B, int ldb, float *C, int ldc, const GemmEpilogue &ep);
+int gemm_dispatch(b200_ctx *ctx, int transA, int transB, int M, int N, int K, const float *A,
+                  int lda, const float *B, int ldb, float *C, int ldc, const GemmEpilogue &ep);
+void gemm_tc_destroy(b200_ctx *ctx);
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}

@@ -1,0 +1,359 @@
+// Host-side C++ mirror of the reference's plugin interfaces for the training hot path:
+//   ANN::ANNComponent            packages/ann/ann/c_src/ann_component.h:95-606
+//   ANN::LossFunction            packages/ann/loss/c_src/loss_function.h:34-120
+//   ann.optimizer.sgd            packages/ann/optimizer/lua_src/optimizer_sgd.lua
+//   trainable.supervised_trainer packages/trainable/lua_src/supervised.lua
+//   Basics::MTRand               packages/basics/random/c_src/MersenneTwister.h
+// Same method names, argument meaning and error behaviour; everything below a Matrix is
+// a call into the C ABI of include/b200ann.h (no CPU fallback: without a device,
+// construction of a Context fails).
+#pragma once
+#include <stdint.h>
+
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../../include/b200ann.h"
+
+namespace b200 {
+
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string &m) : std::runtime_error(m), code(c) {}
+};
+void check(int status);  // throws Error(status, b200_last_error_string())
+
+// ---------------------------------------------------------------- MTRand
+class MTRand {
+ public:
+  explicit MTRand(uint32_t seed) { this->seed(seed); }
+  void seed(uint32_t s);
+  uint32_t randInt();
+  uint32_t randInt(uint32_t n);          // [0, n]
+  double rand(double n = 1.0);           // [0, n]
+  void shuffle(int size, int *out);      // 0-based permutation
+ private:
+  void reload();
+  uint32_t state[624];
+  int left = 0, pos = 0;
+};
+
+// ---------------------------------------------------------------- Matrix
+// Device-resident float32 tensor, contiguous row-major.  Mirrors the part of
+// Basics::Matrix<float> (packages/basics/matrix/c_src/matrix.h:77) the hot path uses.
+class Matrix;
+using MatrixPtr = std::shared_ptr<Matrix>;
+class Matrix : public std::enable_shared_from_this<Matrix> {
+ public:
+  b200_ctx *ctx;
+  std::vector<int> dims;
+  float *data = nullptr;
+  bool owns = false;        // allocated from the pool (freed in the destructor)
+  MatrixPtr parent;         // keeps a viewed block alive
+  int shared_count = 0;     // matrix.h:637-643
+  bool fresh = true;        // gradient accumulators: nothing written yet this step
+
+  static MatrixPtr create(b200_ctx *ctx, const std::vector<int> &dims);
+  static MatrixPtr view(const MatrixPtr &parent, size_t offset, const std::vector<int> &dims);
+  static MatrixPtr wrap(b200_ctx *ctx, float *ptr, const std::vector<int> &dims);
+  ~Matrix();
+  size_t size() const;
+  int dim(int i) const { return dims.at(i); }
+  int rows() const { return dims.at(0); }
+  int cols() const { return (int)(size() / (size_t)dims.at(0)); }
+  MatrixPtr rewrap(const std::vector<int> &new_dims);   // metadata-only reshape
+  void zeros();
+  void fromHost(const float *src);      // async H2D on the context stream
+  void toHost(float *dst) const;        // D2H + sync
+  void copyFrom(const Matrix &o);
+};
+
+using MatrixDict = std::map<std::string, MatrixPtr>;
+void registerCapturedMatrix(const MatrixPtr &m);   // keeps step activations alive for captured graphs
+
+// ---------------------------------------------------------------- components
+class ANNComponent;
+using ComponentPtr = std::shared_ptr<ANNComponent>;
+using ComponentDict = std::map<std::string, ANNComponent *>;
+
+class ANNComponent {
+ public:
+  ANNComponent(const std::string &name, const std::string &weights_name, unsigned in, unsigned out)
+      : name(name), weights_name(weights_name), input_size(in), output_size(out) {}
+  virtual ~ANNComponent() {}
+  // ann_component.h: doForward / doBackprop / computeAllGradients / reset / build
+  virtual MatrixPtr doForward(const MatrixPtr &input, bool during_training) = 0;
+  virtual MatrixPtr doBackprop(const MatrixPtr &error_input) = 0;
+  virtual void computeAllGradients(MatrixDict &grads) {}
+  virtual void reset(unsigned it = 0);
+  virtual void build(unsigned in, unsigned out, MatrixDict &weights, ComponentDict &components);
+  virtual const char *kind() const = 0;
+  virtual bool hasWeightsName() const { return !weights_name.empty(); }
+  virtual void setContext(b200_ctx *c) { ctx = c; }
+
+  const std::string &getName() const { return name; }
+  const std::string &getWeightsName() const { return weights_name; }
+  unsigned getInputSize() const { return input_size; }
+  unsigned getOutputSize() const { return output_size; }
+  MatrixPtr getInput() const { return input; }
+  MatrixPtr getOutput() const { return output; }
+  MatrixPtr getErrorInput() const { return error_input; }
+  MatrixPtr getErrorOutput() const { return error_output; }
+
+  // 1/sqrt(shared_count*bunch) is folded into the gradient kernels; the trainer sets
+  // the bunch factor before computeAllGradients (supervised.lua:797-803).
+  float grad_bunch = 0.0f;   // 0 => unscaled sums (raw component API)
+  float grad_scale = 1.0f;   // set by the enclosing stack: 1/sqrt(total shared count * grad_bunch)
+  // uses of the weights this component adds per step (dot_product_component.cc:177 adds 1,
+  // convolution_component.cc:302 adds the number of output pixels)
+  virtual int sharedCountContribution() const { return 0; }
+
+  std::string name, weights_name;
+  unsigned input_size, output_size;
+  b200_ctx *ctx = nullptr;
+  MatrixPtr input, output, error_input, error_output;
+};
+
+class DotProductANNComponent : public ANNComponent {
+ public:
+  DotProductANNComponent(const std::string &name, const std::string &wname, unsigned in, unsigned out);
+  MatrixPtr doForward(const MatrixPtr &input, bool during_training) override;
+  MatrixPtr doBackprop(const MatrixPtr &error_input) override;
+  void computeAllGradients(MatrixDict &grads) override;
+  void reset(unsigned it = 0) override;
+  void build(unsigned in, unsigned out, MatrixDict &weights, ComponentDict &components) override;
+  const char *kind() const override { return "dot_product"; }
+  int sharedCountContribution() const override { return 1; }
+  MatrixPtr weights_matrix;
+};
+
+class BiasANNComponent : public ANNComponent {
+ public:
+  BiasANNComponent(const std::string &name, const std::string &wname, unsigned size);
+  MatrixPtr doForward(const MatrixPtr &input, bool during_training) override;
+  MatrixPtr doBackprop(const MatrixPtr &error_input) override;
+  void computeAllGradients(MatrixDict &grads) override;
+  void reset(unsigned it = 0) override;
+  void build(unsigned in, unsigned out, MatrixDict &weights, ComponentDict &components) override;
+  const char *kind() const override { return "bias"; }
+  int sharedCountContribution() const override { return 1; }
+  MatrixPtr bias_vector;
+};
+
+class ActivationFunctionANNComponent : public ANNComponent {
+ public:
+  ActivationFunctionANNComponent(const std::string &name, int act);
+  MatrixPtr doForward(const MatrixPtr &input, bool during_training) override;
+  MatrixPtr doBackprop(const MatrixPtr &error_input) override;
+  const char *kind() const override { return "actf"; }
+  void build(unsigned in, unsigned out, MatrixDict &weights, ComponentDict &components) override;
+  bool elementwise() const {
+    return act == B200_ACT_LOGISTIC || act == B200_ACT_TANH || act == B200_ACT_RELU || act == B200_ACT_LINEAR;
+  }
+  int act;
+};
+
+class RewrapANNComponent : public ANNComponent {
+ public:
+  RewrapANNComponent(const std::string &name, const std::vector<int> &size);
+  MatrixPtr doForward(const MatrixPtr &input, bool during_training) override;
+  MatrixPtr doBackprop(const MatrixPtr &error_input) override;
+  void build(unsigned in, unsigned out, MatrixDict &weights, ComponentDict &components) override;
+  const char *kind() const override { return "rewrap"; }
+  std::vector<int> size;
+};
+
+class FlattenANNComponent : public ANNComponent {
+ public:
+  explicit FlattenANNComponent(const std::string &name) : ANNComponent(name, "", 0, 0) {}
+  MatrixPtr doForward(const MatrixPtr &input, bool during_training) override;
+  MatrixPtr doBackprop(const MatrixPtr &error_input) override;
+  const char *kind() const override { return "flatten"; }
+};
+
+class ConvolutionANNComponent : public ANNComponent {
+ public:
+  ConvolutionANNComponent(const std::string &name, const std::string &wname, const std::vector<int> &kernel,
+                          const std::vector<int> &step, int n);
+  MatrixPtr doForward(const MatrixPtr &input, bool during_training) override;
+  MatrixPtr doBackprop(const MatrixPtr &error_input) override;
+  void computeAllGradients(MatrixDict &grads) override;
+  void reset(unsigned it = 0) override;
+  void build(unsigned in, unsigned out, MatrixDict &weights, ComponentDict &components) override;
+  const char *kind() const override { return "convolution"; }
+  int sharedCountContribution() const override { return number_input_windows; }
+  std::vector<int> kernel, step;
+  int n;
+  int number_input_windows = 0;
+  MatrixPtr weights_matrix;
+};
+
+class ConvolutionBiasANNComponent : public ANNComponent {
+ public:
+  ConvolutionBiasANNComponent(const std::string &name, const std::string &wname, int n);
+  MatrixPtr doForward(const MatrixPtr &input, bool during_training) override;
+  MatrixPtr doBackprop(const MatrixPtr &error_input) override;
+  void computeAllGradients(MatrixDict &grads) override;
+  void reset(unsigned it = 0) override;
+  void build(unsigned in, unsigned out, MatrixDict &weights, ComponentDict &components) override;
+  const char *kind() const override { return "convolution_bias"; }
+  int sharedCountContribution() const override { return number_input_windows; }
+  int n;
+  int number_input_windows = 0;
+  MatrixPtr bias_vector;
+};
+
+class MaxPoolingANNComponent : public ANNComponent {
+ public:
+  MaxPoolingANNComponent(const std::string &name, const std::vector<int> &kernel, const std::vector<int> &step);
+  ~MaxPoolingANNComponent();
+  MatrixPtr doForward(const MatrixPtr &input, bool during_training) override;
+  MatrixPtr doBackprop(const MatrixPtr &error_input) override;
+  void reset(unsigned it = 0) override;
+  const char *kind() const override { return "max_pooling"; }
+  std::vector<int> kernel, step;
+  int32_t *argmax = nullptr;
+  size_t argmax_n = 0;
+};
+
+// stack_component.cc:81-104, with hyperplane_component.cc:77-97 flattened into it.
+// Recognised runs (dot_product [+ bias] [+ element-wise actf], convolution [+ convolution_bias]
+// [+ element-wise actf]) execute as one fused launch; anything else runs component by component.
+class StackANNComponent : public ANNComponent {
+ public:
+  explicit StackANNComponent(const std::string &name) : ANNComponent(name, "", 0, 0) {}
+  void pushComponent(const ComponentPtr &c) { components.push_back(c); }
+  MatrixPtr doForward(const MatrixPtr &input, bool during_training) override;
+  MatrixPtr doBackprop(const MatrixPtr &error_input) override;
+  void computeAllGradients(MatrixDict &grads) override;
+  void reset(unsigned it = 0) override;
+  void build(unsigned in, unsigned out, MatrixDict &weights, ComponentDict &components) override;
+  const char *kind() const override { return "stack"; }
+  void setContext(b200_ctx *c) override;
+  std::vector<ComponentPtr> components;   // as pushed (hyperplanes are nested stacks)
+  bool fuse = true;                       // false: run every component separately (all tokens observable)
+  bool skip_input_gradient = false;       // trainer: the network-input gradient is never used
+  ANNComponent *lastComponent();
+  // set by the trainer when the loss kernel already produced d(loss)/d(pre-activation)
+  bool last_actf_backprop_is_identity = false;
+  // set by the trainer: stop before a trailing row-wise activation so that the loss kernel
+  // can fuse log_softmax + loss + gradient
+  bool defer_last_actf = false;
+ private:
+  void flatten(std::vector<ANNComponent *> &out);
+  std::vector<ANNComponent *> flat;
+  friend class SupervisedTrainer;
+};
+
+ComponentPtr makeHyperplane(const std::string &name, unsigned in, unsigned out, const std::string &dot_name,
+                            const std::string &bias_name, const std::string &dot_weights,
+                            const std::string &bias_weights);
+// ann.mlp.all_all.generate  (packages/ann/ann/lua_src/annbase.lua:509-660)
+std::shared_ptr<StackANNComponent> mlpAllAllGenerate(const std::string &topology);
+int actfFromName(const std::string &kind);   // throws on unknown names
+
+// ---------------------------------------------------------------- loss
+enum LossKind { LOSS_MSE = 0, LOSS_CROSS_ENTROPY = 1, LOSS_MULTI_CLASS_CROSS_ENTROPY = 2 };
+
+class LossFunction {
+ public:
+  LossFunction(b200_ctx *ctx, int kind, unsigned size);
+  ~LossFunction();
+  // computeLoss: per-pattern loss vector [bunch] on the device (loss_function.h:109-113)
+  MatrixPtr computeLoss(const MatrixPtr &input, const MatrixPtr &target);
+  MatrixPtr computeGradient(const MatrixPtr &input, const MatrixPtr &target);
+  // fused log_softmax + MCCE: logits -> (logp, loss rows, gradient) in one pass
+  void fusedLogSoftmaxMCCE(const MatrixPtr &logits, const MatrixPtr &target, MatrixPtr &logp,
+                           MatrixPtr &loss_rows, MatrixPtr &grad);
+  void accumLoss(const MatrixPtr &loss_rows);       // device-side running statistics
+  void getAccumLoss(float *mean, float *variance);  // one D2H of 3 doubles (loss_function.h:90-95)
+  void reset();
+  int kind;
+  unsigned size;
+  b200_ctx *ctx;
+  double *stats_dev = nullptr;   // sum, sum of squares, count
+};
+
+// ---------------------------------------------------------------- optimizer
+class SGDOptimizer {
+ public:
+  SGDOptimizer();
+  void setOption(const std::string &name, double v);
+  double getOption(const std::string &name) const;
+  void setLayerwiseOption(const std::string &layer, const std::string &name, double v);
+  double getOptionOf(const std::string &layer, const std::string &name) const;
+  std::map<std::string, double> global_options;
+  std::map<std::string, std::map<std::string, double>> layerwise_options;
+  int64_t count = 0;     // host mirror of the device counter
+};
+
+// ---------------------------------------------------------------- trainer
+class SupervisedTrainer {
+ public:
+  SupervisedTrainer(b200_ctx *ctx, const std::shared_ptr<StackANNComponent> &net, int loss_kind, int bunch_size);
+  ~SupervisedTrainer();
+  void build(unsigned input = 0, unsigned output = 0);
+  void setOption(const std::string &name, double v);
+  double getOption(const std::string &name) const { return optimizer.getOption(name); }
+  void setLayerwiseOption(const std::string &pattern, const std::string &name, double v);
+  void randomizeWeights(MTRand &rnd, double inf, double sup, bool use_fanin, bool use_fanout,
+                        const std::string &name_match);
+  // one training step on a device-resident bunch; returns nothing on the host (the per-row
+  // losses stay on the device in last_loss_rows).  supervised.lua:725-821
+  void trainStepDevice(const MatrixPtr &x, const MatrixPtr &t);
+  void validateStepDevice(const MatrixPtr &x, const MatrixPtr &t);
+  // host-pointer API: H2D of the bunch, step, D2H of the bunch-mean loss
+  float trainStep(const float *x, const float *t, int bunch, float *loss_rows_out);
+  float validateStep(const float *x, const float *t, int bunch, float *loss_rows_out);
+  // dataset loops (supervised.lua:1149-1226, trainable.lua:95-330): the dataset is uploaded
+  // once, bunches are gathered on the device, the epoch mean is read back once.
+  void trainDataset(const float *x, const float *t, int n, const int *order, float *mean, float *var);
+  void validateDataset(const float *x, const float *t, int n, float *mean, float *var);
+  MatrixPtr calculate(const MatrixPtr &x);
+  void stage(const float *x, const float *t, int bunch);   // async H2D into the staging buffers
+  void stepStaged(int bunch);                              // train step on the staged bunch
+  std::vector<std::string> weightNames() const { return weights_order; }
+  MatrixPtr weight(const std::string &n) { return weights_table.at(n); }
+  MatrixPtr gradient(const std::string &n) { return grads.at(n); }
+  double norm2(const std::string &pattern);
+
+  // data-parallel replica group (weights identical on every rank; gradients summed)
+  void setDataParallel(int nranks, int rank) { dp_nranks = nranks; dp_rank = rank; }
+  void broadcastWeights();
+
+  b200_ctx *ctx;
+  std::shared_ptr<StackANNComponent> net;
+  LossFunction loss;
+  SGDOptimizer optimizer;
+  int bunch_size;
+  bool smooth_gradients = true;
+  bool keep_gradients = false;    // write the regularised gradient back (observable grads; +4 B/param)
+  bool use_cuda_graph = true;
+  MatrixDict weights_table, grads, updates;
+  std::vector<std::string> weights_order;
+  MatrixPtr weights_arena, grads_arena, updates_arena;
+  MatrixPtr last_loss_rows, last_output;
+  int dp_nranks = 1, dp_rank = 0;
+  int64_t *count_dev = nullptr;
+  size_t numParameters() const { return total_params; }
+
+ private:
+  void runStep(const MatrixPtr &x, const MatrixPtr &t, int global_bunch);
+  void uploadSgdTable();
+  size_t total_params = 0;
+  b200_sgd_tensor *sgd_dev = nullptr;
+  std::vector<b200_sgd_tensor> sgd_host;
+  bool sgd_dirty = true;
+  std::string sgd_signature;
+  // staging + device-resident dataset
+  MatrixPtr stage_x, stage_t;
+  struct Graph;
+  std::map<int, Graph *> graphs;   // bunch size -> captured step
+};
+
+bool luaPatternMatch(const std::string &pattern, const std::string &s);
+
+}  // namespace b200

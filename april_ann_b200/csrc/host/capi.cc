@@ -1,0 +1,256 @@
+// extern "C" surface of the host mirror (include/b200ann_host.h): opaque handles over the
+// C++ classes of ann.h, exceptions turned into status codes + b200_last_error_string().
+#include <string.h>
+
+#include "../../../include/b200ann_host.h"
+#include "ann.h"
+
+void b200_set_error(const char *fmt, ...);
+
+using namespace b200;
+
+struct b200_component { ComponentPtr c; };
+struct b200_trainer { SupervisedTrainer *t; std::shared_ptr<StackANNComponent> net; };
+struct b200_random { MTRand r; explicit b200_random(uint32_t s) : r(s) {} };
+
+#define API_TRY(body)                                  \
+  try {                                                \
+    body;                                              \
+    return B200_OK;                                    \
+  } catch (const Error &e) {                           \
+    b200_set_error("%s", e.what());                    \
+    return e.code ? e.code : B200_ERR_BAD_ARG;         \
+  } catch (const std::exception &e) {                  \
+    b200_set_error("%s", e.what());                    \
+    return B200_ERR_BAD_ARG;                           \
+  }
+
+static b200_component *wrap(const ComponentPtr &c) { return new b200_component{c}; }
+static std::string str(const char *s) { return s ? std::string(s) : std::string(); }
+template <class F>
+static b200_component *make(F f) {
+  try {
+    return wrap(f());
+  } catch (const std::exception &e) {
+    b200_set_error("%s", e.what());
+    return nullptr;
+  }
+}
+
+extern "C" {
+
+b200_random *b200h_random_new(uint32_t seed) { return new b200_random(seed); }
+void b200h_random_free(b200_random *r) { delete r; }
+double b200h_random_rand(b200_random *r, double n) { return r->r.rand(n); }
+uint32_t b200h_random_randint(b200_random *r, uint32_t n) { return r->r.randInt(n); }
+int b200h_random_shuffle(b200_random *r, int size, int *out) {
+  if (!r || !out || size <= 0) { b200_set_error("random shuffle: size must be >= 0"); return B200_ERR_BAD_ARG; }
+  r->r.shuffle(size, out);
+  return B200_OK;
+}
+
+b200_component *b200h_stack_new(const char *name) {
+  return make([&] { return std::make_shared<StackANNComponent>(str(name)); });
+}
+int b200h_stack_push(b200_component *stack, b200_component *child) {
+  API_TRY({
+    auto *s = stack ? dynamic_cast<StackANNComponent *>(stack->c.get()) : nullptr;
+    if (!s || !child) throw Error(B200_ERR_BAD_ARG, "stack push: not a stack / NULL child");
+    s->pushComponent(child->c);
+  })
+}
+b200_component *b200h_hyperplane_new(const char *name, unsigned in, unsigned out, const char *dot_name,
+                                     const char *bias_name, const char *dot_weights, const char *bias_weights) {
+  return make([&] { return makeHyperplane(str(name), in, out, str(dot_name), str(bias_name), str(dot_weights), str(bias_weights)); });
+}
+b200_component *b200h_dot_product_new(const char *name, const char *weights, unsigned in, unsigned out) {
+  return make([&] { return std::make_shared<DotProductANNComponent>(str(name), str(weights), in, out); });
+}
+b200_component *b200h_bias_new(const char *name, const char *weights, unsigned size) {
+  return make([&] { return std::make_shared<BiasANNComponent>(str(name), str(weights), size); });
+}
+b200_component *b200h_actf_new(const char *kind, const char *name) {
+  return make([&] { return std::make_shared<ActivationFunctionANNComponent>(str(name), actfFromName(str(kind))); });
+}
+b200_component *b200h_rewrap_new(const char *name, const int *size, int ndims) {
+  return make([&] { return std::make_shared<RewrapANNComponent>(str(name), std::vector<int>(size, size + ndims)); });
+}
+b200_component *b200h_flatten_new(const char *name) {
+  return make([&] { return std::make_shared<FlattenANNComponent>(str(name)); });
+}
+b200_component *b200h_convolution_new(const char *name, const char *weights, const int *kernel, const int *step,
+                                      int ndims, int n) {
+  return make([&] {
+    std::vector<int> k(kernel, kernel + ndims), s;
+    if (step) s.assign(step, step + ndims);
+    return std::make_shared<ConvolutionANNComponent>(str(name), str(weights), k, s, n);
+  });
+}
+b200_component *b200h_convolution_bias_new(const char *name, const char *weights, int n) {
+  return make([&] { return std::make_shared<ConvolutionBiasANNComponent>(str(name), str(weights), n); });
+}
+b200_component *b200h_max_pooling_new(const char *name, const int *kernel, const int *step, int ndims) {
+  return make([&] {
+    std::vector<int> k(kernel, kernel + ndims), s;
+    if (step) s.assign(step, step + ndims);
+    return std::make_shared<MaxPoolingANNComponent>(str(name), k, s);
+  });
+}
+b200_component *b200h_mlp_generate(const char *topology) {
+  return make([&] { return mlpAllAllGenerate(str(topology)); });
+}
+void b200h_component_free(b200_component *c) { delete c; }
+
+b200_trainer *b200h_trainer_new(b200_ctx *ctx, b200_component *net, int loss_kind, int bunch_size) {
+  try {
+    auto s = net ? std::dynamic_pointer_cast<StackANNComponent>(net->c) : nullptr;
+    if (!s) {
+      // a single component is wrapped in a stack, as the trainer only drives stacks
+      if (!net) throw Error(B200_ERR_BAD_ARG, "trainer: NULL component");
+      s = std::make_shared<StackANNComponent>("stack");
+      s->pushComponent(net->c);
+    }
+    auto *t = new b200_trainer{nullptr, s};
+    t->t = new SupervisedTrainer(ctx, s, loss_kind, bunch_size);
+    return t;
+  } catch (const std::exception &e) {
+    b200_set_error("%s", e.what());
+    return nullptr;
+  }
+}
+void b200h_trainer_free(b200_trainer *t) {
+  if (!t) return;
+  delete t->t;
+  delete t;
+}
+int b200h_trainer_build(b200_trainer *t, unsigned input, unsigned output) { API_TRY(t->t->build(input, output)) }
+int b200h_trainer_set_option(b200_trainer *t, const char *name, double v) { API_TRY(t->t->setOption(str(name), v)) }
+int b200h_trainer_get_option(b200_trainer *t, const char *name, double *v) { API_TRY(*v = t->t->getOption(str(name))) }
+int b200h_trainer_set_layerwise_option(b200_trainer *t, const char *pattern, const char *name, double v) {
+  API_TRY(t->t->setLayerwiseOption(str(pattern), str(name), v))
+}
+int b200h_trainer_randomize_weights(b200_trainer *t, b200_random *rnd, double inf, double sup, int use_fanin,
+                                    int use_fanout, const char *name_match) {
+  API_TRY({
+    if (!rnd) throw Error(B200_ERR_BAD_ARG, "randomize_weights: random object is mandatory");
+    t->t->randomizeWeights(rnd->r, inf, sup, use_fanin != 0, use_fanout != 0, str(name_match));
+  })
+}
+int b200h_trainer_set_flag(b200_trainer *t, const char *flag, int value) {
+  API_TRY({
+    std::string f = str(flag);
+    if (f == "fuse") t->net->fuse = value != 0;
+    else if (f == "cuda_graph") t->t->use_cuda_graph = value != 0;
+    else if (f == "keep_gradients") t->t->keep_gradients = value != 0;
+    else if (f == "smooth_gradients") t->t->smooth_gradients = value != 0;
+    else throw Error(B200_ERR_BAD_ARG, "unknown flag " + f);
+  })
+}
+int b200h_trainer_num_weights(b200_trainer *t, int *n) { API_TRY(*n = (int)t->t->weights_order.size()) }
+int b200h_trainer_weight_name(b200_trainer *t, int i, char *buf, int buflen) {
+  API_TRY({
+    const std::string &s = t->t->weights_order.at(i);
+    if ((int)s.size() + 1 > buflen) throw Error(B200_ERR_BAD_ARG, "buffer too small");
+    memcpy(buf, s.c_str(), s.size() + 1);
+  })
+}
+int b200h_trainer_weight_dims(b200_trainer *t, const char *name, int *dims2) {
+  API_TRY({
+    MatrixPtr w = t->t->weights_table.at(str(name));
+    dims2[0] = w->dim(0);
+    dims2[1] = w->cols();
+  })
+}
+static MatrixPtr pick(b200_trainer *t, const char *name, int which) {
+  MatrixDict &d = which == 0 ? t->t->weights_table : (which == 1 ? t->t->grads : t->t->updates);
+  auto it = d.find(str(name));
+  if (it == d.end()) throw Error(B200_ERR_BAD_ARG, "unknown weights name " + str(name));
+  return it->second;
+}
+int b200h_trainer_tensor_get(b200_trainer *t, const char *name, int which, float *host) {
+  API_TRY(pick(t, name, which)->toHost(host))
+}
+int b200h_trainer_tensor_set(b200_trainer *t, const char *name, int which, const float *host) {
+  API_TRY({
+    MatrixPtr m = pick(t, name, which);
+    m->fromHost(host);
+    check(b200_sync(t->t->ctx));
+  })
+}
+int b200h_trainer_num_parameters(b200_trainer *t, uint64_t *n) { API_TRY(*n = t->t->numParameters()) }
+int b200h_trainer_input_size(b200_trainer *t, int *n) { API_TRY(*n = (int)t->net->getInputSize()) }
+int b200h_trainer_output_size(b200_trainer *t, int *n) { API_TRY(*n = (int)t->net->getOutputSize()) }
+
+int b200h_trainer_train_step(b200_trainer *t, const float *x, const float *target, int bunch, float *loss,
+                             float *loss_rows) {
+  API_TRY({
+    float l = t->t->trainStep(x, target, bunch, loss_rows);
+    if (loss) *loss = l;
+  })
+}
+int b200h_trainer_validate_step(b200_trainer *t, const float *x, const float *target, int bunch, float *loss,
+                                float *loss_rows) {
+  API_TRY({
+    float l = t->t->validateStep(x, target, bunch, loss_rows);
+    if (loss) *loss = l;
+  })
+}
+int b200h_trainer_train_dataset(b200_trainer *t, const float *x, const float *target, int n, const int *order,
+                                float *mean, float *variance) {
+  API_TRY(t->t->trainDataset(x, target, n, order, mean, variance))
+}
+int b200h_trainer_validate_dataset(b200_trainer *t, const float *x, const float *target, int n, float *mean,
+                                   float *variance) {
+  API_TRY(t->t->validateDataset(x, target, n, mean, variance))
+}
+int b200h_trainer_calculate(b200_trainer *t, const float *x, int bunch, float *y) {
+  API_TRY({
+    const int in = (int)t->net->getInputSize();
+    MatrixPtr dx = Matrix::create(t->t->ctx, std::vector<int>{bunch, in});
+    dx->fromHost(x);
+    MatrixPtr out = t->t->calculate(dx);
+    out->toHost(y);
+  })
+}
+int b200h_trainer_component_token(b200_trainer *t, const char *component, int which, float *data, int *dims,
+                                  int *ndims) {
+  API_TRY({
+    ComponentDict comps;
+    MatrixDict w = t->t->weights_table;
+    ANNComponent *found = nullptr;
+    std::vector<ANNComponent *> todo{t->net.get()};
+    while (!todo.empty() && !found) {
+      ANNComponent *c = todo.back();
+      todo.pop_back();
+      if (c->getName() == str(component)) found = c;
+      if (auto *s = dynamic_cast<StackANNComponent *>(c))
+        for (auto &k : s->components) todo.push_back(k.get());
+    }
+    if (!found) throw Error(B200_ERR_BAD_ARG, "unknown component " + str(component));
+    MatrixPtr m = which == B200_TOKEN_INPUT ? found->getInput()
+                  : which == B200_TOKEN_OUTPUT ? found->getOutput()
+                  : which == B200_TOKEN_ERROR_INPUT ? found->getErrorInput()
+                                                    : found->getErrorOutput();
+    if (!m) throw Error(B200_ERR_BAD_ARG, "token not materialised (inside a fused run; set flag fuse=0)");
+    *ndims = (int)m->dims.size();
+    for (int i = 0; i < *ndims && i < 4; ++i) dims[i] = m->dims[i];
+    if (data) m->toHost(data);
+  })
+}
+int b200h_trainer_stage(b200_trainer *t, const float *x, const float *target, int bunch) {
+  API_TRY(t->t->stage(x, target, bunch))
+}
+int b200h_trainer_step_staged(b200_trainer *t, int bunch) { API_TRY(t->t->stepStaged(bunch)) }
+int b200h_trainer_loss_reset(b200_trainer *t) { API_TRY(t->t->loss.reset()) }
+int b200h_trainer_loss_get(b200_trainer *t, float *mean, float *variance) {
+  API_TRY(t->t->loss.getAccumLoss(mean, variance))
+}
+int b200h_trainer_last_loss_async(b200_trainer *t, double *pinned_out) {
+  API_TRY(check(b200_memcpy_d2h(t->t->ctx, pinned_out, t->t->loss.stats_dev + 3, sizeof(double))))
+}
+int b200h_trainer_set_data_parallel(b200_trainer *t, int nranks, int rank) {
+  API_TRY(t->t->setDataParallel(nranks, rank))
+}
+int b200h_trainer_broadcast_weights(b200_trainer *t) { API_TRY(t->t->broadcastWeights()) }
+
+}  // extern "C"

@@ -1,0 +1,524 @@
+// Loss functions, SGD options and the supervised trainer of the host mirror.
+//   ann.loss.*                   packages/ann/loss/c_src/*_loss_function.cc, loss_function.h:34-120
+//   ann.optimizer.sgd            packages/ann/optimizer/lua_src/optimizer_sgd.lua:22-100
+//   trainable.supervised_trainer packages/trainable/lua_src/supervised.lua:575-862,1149-1430
+// The whole train step (forward, loss, backward, weight gradients, [all-reduce], SGD, loss
+// statistics, step counter) is enqueued on one stream and, once warm, replayed as a CUDA graph.
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include <algorithm>
+
+#include "../../../include/b200ann_host.h"
+#include "ann.h"
+
+namespace b200 {
+
+static void cudaCheck(cudaError_t e, const char *what) {
+  if (e != cudaSuccess) throw Error(B200_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+// matrices created while a step is being captured must outlive the graph
+static thread_local std::vector<MatrixPtr> *g_capture_registry = nullptr;
+void registerCapturedMatrix(const MatrixPtr &m) {
+  if (g_capture_registry) g_capture_registry->push_back(m);
+}
+
+// ------------------------------------------------------------------ loss
+LossFunction::LossFunction(b200_ctx *ctx, int kind, unsigned size) : kind(kind), size(size), ctx(ctx) {
+  if (kind == LOSS_MULTI_CLASS_CROSS_ENTROPY && size > 0 && size < 3)
+    throw Error(128, "Multi class cross entropy is only allowed for multi-class problems (three or more output "
+                     "log softmax neurons). Use cross entropy instead.");
+  void *p;
+  check(b200_malloc(ctx, &p, 4 * sizeof(double)));
+  stats_dev = (double *)p;
+  reset();
+}
+LossFunction::~LossFunction() {
+  if (stats_dev) b200_free(ctx, stats_dev);
+}
+void LossFunction::reset() { check(b200_memset_zero(ctx, stats_dev, 4 * sizeof(double))); }
+
+static void checkLossArgs(const LossFunction &l, const MatrixPtr &in, const MatrixPtr &tg) {
+  if (!in || !tg) throw Error(128, "Incorrect input token type, expected token matrix");
+  if (in->size() != tg->size()) throw Error(128, "Different token sizes found: input vs target");
+  if (in->dims.size() != 2) throw Error(128, "loss input must be a 2-dimensional matrix");
+  if (l.size != 0 && (unsigned)in->cols() != l.size) throw Error(128, "loss input size mismatch");
+}
+MatrixPtr LossFunction::computeLoss(const MatrixPtr &in, const MatrixPtr &tg) {
+  checkLossArgs(*this, in, tg);
+  MatrixPtr rows = Matrix::create(ctx, std::vector<int>{in->rows()});
+  const int M = in->rows(), C = in->cols();
+  if (kind == LOSS_MSE) check(b200_mse_loss_grad(ctx, M, C, in->data, tg->data, rows->data, nullptr));
+  else if (kind == LOSS_CROSS_ENTROPY) check(b200_ce_loss_grad(ctx, M, C, in->data, tg->data, rows->data, nullptr));
+  else check(b200_mcce_loss_grad(ctx, M, C, in->data, tg->data, rows->data, nullptr));
+  return rows;
+}
+MatrixPtr LossFunction::computeGradient(const MatrixPtr &in, const MatrixPtr &tg) {
+  checkLossArgs(*this, in, tg);
+  MatrixPtr g = Matrix::create(ctx, in->dims);
+  const int M = in->rows(), C = in->cols();
+  if (kind == LOSS_MSE) check(b200_mse_loss_grad(ctx, M, C, in->data, tg->data, nullptr, g->data));
+  else if (kind == LOSS_CROSS_ENTROPY) check(b200_ce_loss_grad(ctx, M, C, in->data, tg->data, nullptr, g->data));
+  else check(b200_mcce_loss_grad(ctx, M, C, in->data, tg->data, nullptr, g->data));
+  return g;
+}
+void LossFunction::fusedLogSoftmaxMCCE(const MatrixPtr &logits, const MatrixPtr &tg, MatrixPtr &logp,
+                                       MatrixPtr &rows, MatrixPtr &grad) {
+  checkLossArgs(*this, logits, tg);
+  const int M = logits->rows(), C = logits->cols();
+  if (!logp) logp = Matrix::create(ctx, logits->dims);
+  rows = Matrix::create(ctx, std::vector<int>{M});
+  check(b200_log_softmax_mcce_fused(ctx, M, C, logits->data, tg->data, logp->data, rows->data,
+                                    grad ? grad->data : nullptr));
+}
+void LossFunction::accumLoss(const MatrixPtr &rows) {
+  check(b200_loss_accumulate(ctx, (int)rows->size(), rows->data, stats_dev));
+}
+void LossFunction::getAccumLoss(float *mean, float *variance) {
+  double h[4];
+  check(b200_memcpy_d2h(ctx, h, stats_dev, 3 * sizeof(double)));
+  check(b200_sync(ctx));
+  const double n = h[2];
+  const double m = n > 0 ? h[0] / n : 0.0;
+  double v = n > 1 ? (h[1] - h[0] * h[0] / n) / (n - 1) : 0.0;
+  if (v < 0) v = 0;
+  if (mean) *mean = (float)m;
+  if (variance) *variance = (float)v;
+}
+
+// ------------------------------------------------------------------ optimizer options
+static const char *kSgdOptions[] = {"learning_rate", "momentum", "decay", "weight_decay", "L1_norm", "max_norm_penalty"};
+static bool validOption(const std::string &n) {
+  for (const char *o : kSgdOptions)
+    if (n == o) return true;
+  return false;
+}
+SGDOptimizer::SGDOptimizer() {
+  // optimizer_sgd.lua:39-47
+  global_options = {{"learning_rate", 0.01}, {"momentum", 0.0}, {"decay", 1e-05},
+                    {"weight_decay", 0.0},   {"L1_norm", 0.0},  {"max_norm_penalty", 0.0}};
+}
+void SGDOptimizer::setOption(const std::string &n, double v) {
+  if (!validOption(n)) throw Error(B200_ERR_BAD_ARG, "Not recognized option " + n);
+  global_options[n] = v;
+}
+double SGDOptimizer::getOption(const std::string &n) const {
+  if (!validOption(n)) throw Error(B200_ERR_BAD_ARG, "Not recognized option " + n);
+  return global_options.at(n);
+}
+void SGDOptimizer::setLayerwiseOption(const std::string &layer, const std::string &n, double v) {
+  if (!validOption(n)) throw Error(B200_ERR_BAD_ARG, "Not recognized option " + n);
+  if (n == "decay") throw Error(B200_ERR_BAD_ARG, "decay option cannot be defined layerwise, only globally");
+  layerwise_options[layer][n] = v;
+}
+double SGDOptimizer::getOptionOf(const std::string &layer, const std::string &n) const {
+  auto it = layerwise_options.find(layer);
+  if (it != layerwise_options.end()) {
+    auto jt = it->second.find(n);
+    if (jt != it->second.end()) return jt->second;
+  }
+  return getOption(n);
+}
+
+// ------------------------------------------------------------------ trainer
+struct SupervisedTrainer::Graph {
+  cudaGraphExec_t exec = nullptr;
+  cudaGraph_t graph = nullptr;
+  std::vector<MatrixPtr> keep;
+  MatrixPtr rows, out;
+  const float *x_ptr = nullptr, *t_ptr = nullptr;
+  uint64_t launches = 0;
+  int warm = 0;
+  ~Graph() {
+    if (exec) cudaGraphExecDestroy(exec);
+    if (graph) cudaGraphDestroy(graph);
+  }
+};
+
+SupervisedTrainer::SupervisedTrainer(b200_ctx *ctx, const std::shared_ptr<StackANNComponent> &net, int loss_kind,
+                                     int bunch_size)
+    : ctx(ctx), net(net), loss(ctx, loss_kind, 0), bunch_size(bunch_size) {
+  if (!ctx) throw Error(B200_ERR_CUDA, "trainer needs a device context: this build has no CPU path");
+  void *p;
+  check(b200_malloc(ctx, &p, 2 * sizeof(int64_t)));
+  count_dev = (int64_t *)p;
+  check(b200_memset_zero(ctx, count_dev, 2 * sizeof(int64_t)));
+}
+SupervisedTrainer::~SupervisedTrainer() {
+  b200_sync(ctx);
+  for (auto &kv : graphs) delete kv.second;
+  if (count_dev) b200_free(ctx, count_dev);
+  if (sgd_dev) b200_free(ctx, sgd_dev);
+}
+
+void SupervisedTrainer::build(unsigned input, unsigned output) {
+  net->setContext(ctx);
+  // pass 1: discover weight names and shapes
+  MatrixDict discovered;
+  ComponentDict comps;
+  net->build(input, output, discovered, comps);
+  weights_order.clear();
+  for (auto &kv : discovered) weights_order.push_back(kv.first);
+  std::sort(weights_order.begin(), weights_order.end());  // supervised.lua:680-681
+  // pass 2: re-home every tensor in flat arenas (weights / gradients / momentum), sorted-name
+  // order, 512-byte aligned -- one all-reduce and one SGD launch cover all of them
+  std::vector<size_t> offs;
+  size_t total = 0;
+  for (auto &n : weights_order) {
+    offs.push_back(total);
+    total += (discovered[n]->size() + 127) & ~size_t(127);
+  }
+  total_params = 0;
+  weights_arena = Matrix::create(ctx, std::vector<int>{(int)total});
+  grads_arena = Matrix::create(ctx, std::vector<int>{(int)total});
+  updates_arena = Matrix::create(ctx, std::vector<int>{(int)total});
+  weights_arena->zeros();
+  grads_arena->zeros();
+  updates_arena->zeros();
+  weights_table.clear();
+  grads.clear();
+  updates.clear();
+  for (size_t i = 0; i < weights_order.size(); ++i) {
+    const std::string &n = weights_order[i];
+    const std::vector<int> &d = discovered[n]->dims;
+    weights_table[n] = Matrix::view(weights_arena, offs[i], d);
+    grads[n] = Matrix::view(grads_arena, offs[i], d);
+    updates[n] = Matrix::view(updates_arena, offs[i], d);
+    total_params += discovered[n]->size();
+  }
+  ComponentDict comps2;
+  net->build(input, output, weights_table, comps2);
+  loss.size = 0;
+  sgd_dirty = true;
+  for (auto &kv : graphs) delete kv.second;
+  graphs.clear();
+}
+
+void SupervisedTrainer::setOption(const std::string &name, double v) {
+  optimizer.setOption(name, v);
+  sgd_dirty = true;
+}
+void SupervisedTrainer::setLayerwiseOption(const std::string &pattern, const std::string &name, double v) {
+  // supervised.lua:262-269: the Lua pattern is expanded over the weight names
+  for (auto &n : weights_order)
+    if (luaPatternMatch(pattern, n)) optimizer.setLayerwiseOption(n, name, v);
+  sgd_dirty = true;
+}
+
+void SupervisedTrainer::randomizeWeights(MTRand &rnd, double inf, double sup, bool use_fanin, bool use_fanout,
+                                         const std::string &name_match) {
+  // supervised.lua:575-635 + connection.cc:77-91 (rnd_weight macro :37-46)
+  if (weights_order.empty()) throw Error(B200_ERR_NOT_BUILT, "Execute build method before randomize_weights");
+  for (auto &n : weights_order) {
+    if (!name_match.empty() && !luaPatternMatch(name_match, n)) continue;
+    MatrixPtr w = weights_table[n];
+    double constant = 0;
+    if (use_fanin) constant += w->dim(1);
+    if (use_fanout) constant += w->dim(0);
+    double cinf = inf, csup = sup;
+    if (constant > 0) { cinf = inf / sqrt(constant); csup = sup / sqrt(constant); }
+    double dinf = (double)(float)cinf, dsup = (double)(float)csup;
+    const double nearzero = 1e-7;
+    if (fabs(dinf) < nearzero) dinf = nearzero;
+    if (fabs(dsup) < nearzero) dsup = -nearzero;
+    const double range = dsup - dinf;
+    std::vector<float> host(w->size());
+    for (auto &v : host) {
+      unsigned it = 0;
+      do {
+        v = (float)(rnd.rand(range) + dinf);
+        ++it;
+      } while (it < 1000 && fabs(v) < nearzero);
+    }
+    w->fromHost(host.data());
+    check(b200_sync(ctx));
+  }
+}
+
+void SupervisedTrainer::uploadSgdTable() {
+  const int nt = (int)weights_order.size();
+  sgd_host.resize(nt);
+  for (int i = 0; i < nt; ++i) {
+    const std::string &n = weights_order[i];
+    b200_sgd_tensor &t = sgd_host[i];
+    memset(&t, 0, sizeof(t));
+    t.w = weights_table[n]->data;
+    t.g = grads[n]->data;
+    t.u = updates[n]->data;
+    t.n = weights_table[n]->size();
+    t.rows = weights_table[n]->dim(0);
+    t.cols = weights_table[n]->cols();
+    t.lr = (float)optimizer.getOptionOf(n, "learning_rate");
+    t.momentum = (float)optimizer.getOptionOf(n, "momentum");
+    t.weight_decay = (float)optimizer.getOptionOf(n, "weight_decay");
+    t.l1_norm = (float)optimizer.getOptionOf(n, "L1_norm");
+    t.max_norm_penalty = (float)optimizer.getOptionOf(n, "max_norm_penalty");
+  }
+  if (!sgd_dev) {
+    void *p;
+    check(b200_malloc(ctx, &p, sizeof(b200_sgd_tensor) * (size_t)std::max(nt, 1)));
+    sgd_dev = (b200_sgd_tensor *)p;
+  }
+  check(b200_memcpy_h2d(ctx, sgd_dev, sgd_host.data(), sizeof(b200_sgd_tensor) * (size_t)nt));
+  check(b200_sync(ctx));  // sgd_host may be rewritten before the copy would otherwise run
+  sgd_dirty = false;
+  // captured graphs read the hyper-parameters from the device table, but the max-norm launches
+  // are part of the graph structure: re-capture when that set changes
+  std::string sig;
+  for (auto &t : sgd_host) sig += (t.max_norm_penalty > 0.0f) ? '1' : '0';
+  if (sig != sgd_signature) {
+    for (auto &kv : graphs) delete kv.second;
+    graphs.clear();
+    sgd_signature = sig;
+  }
+}
+
+// One training step enqueued on the stream: supervised.lua:769-819 + optimizer_sgd.lua:50-100.
+void SupervisedTrainer::runStep(const MatrixPtr &x, const MatrixPtr &t, int global_bunch) {
+  net->reset();
+  for (auto &kv : grads) kv.second->fresh = true;
+  auto *last = dynamic_cast<ActivationFunctionANNComponent *>(net->lastComponent());
+  const bool fused_loss =
+      net->fuse && last && last->act == B200_ACT_LOG_SOFTMAX && loss.kind == LOSS_MULTI_CLASS_CROSS_ENTROPY;
+  MatrixPtr out, rows, grad;
+  net->skip_input_gradient = true;
+  if (fused_loss) {
+    net->defer_last_actf = true;
+    MatrixPtr logits = net->doForward(x, true);
+    net->defer_last_actf = false;
+    grad = Matrix::create(ctx, logits->dims);
+    loss.fusedLogSoftmaxMCCE(logits, t, out, rows, grad);
+    last->input = logits;
+    last->output = out;
+    net->output = out;
+    net->last_actf_backprop_is_identity = true;
+  } else {
+    out = net->doForward(x, true);
+    rows = loss.computeLoss(out, t);
+    grad = loss.computeGradient(out, t);
+    net->last_actf_backprop_is_identity = false;
+  }
+  net->doBackprop(grad);
+  net->last_actf_backprop_is_identity = false;
+  net->grad_bunch = smooth_gradients ? (float)global_bunch : 0.0f;
+  net->computeAllGradients(grads);
+  if (dp_nranks > 1) check(b200_allreduce_sum(ctx, grads_arena->data, grads_arena->size()));
+  check(b200_sgd_multi_tensor(ctx, (int)sgd_host.size(), sgd_dev, sgd_host.data(), optimizer.getOption("decay"),
+                              count_dev, keep_gradients ? 1 : 0));
+  check(b200_counter_increment(ctx, count_dev));
+  loss.accumLoss(rows);
+  last_loss_rows = rows;
+  last_output = out;
+}
+
+void SupervisedTrainer::trainStepDevice(const MatrixPtr &x, const MatrixPtr &t) {
+  if (weights_order.empty()) throw Error(B200_ERR_NOT_BUILT, "Execute build method before call this method");
+  if (sgd_dirty) {
+    // hyper-parameters are baked into the SGD table; captured graphs read it from the device
+    uploadSgdTable();
+  }
+  const int bunch = x->rows();
+  const int global_bunch = bunch * dp_nranks;
+  cudaStream_t stream = (cudaStream_t)b200_stream(ctx);
+  Graph *g = nullptr;
+  if (use_cuda_graph) {
+    auto it = graphs.find(bunch);
+    if (it == graphs.end()) {
+      g = new Graph();
+      graphs[bunch] = g;
+    } else {
+      g = it->second;
+    }
+  }
+  if (g && g->exec && g->x_ptr == x->data && g->t_ptr == t->data) {
+    cudaCheck(cudaGraphLaunch(g->exec, stream), "cudaGraphLaunch");
+    b200_add_launches(ctx, g->launches);
+    last_loss_rows = g->rows;
+    last_output = g->out;
+    optimizer.count++;
+    return;
+  }
+  if (g && g->warm >= 1 && !g->exec) {
+    // second step of this bunch size: the pool and scratch are warm, capture it
+    uint64_t before = 0, after = 0;
+    b200_launch_count(ctx, &before);
+    g_capture_registry = &g->keep;
+    cudaCheck(cudaStreamBeginCapture(stream, cudaStreamCaptureModeRelaxed), "cudaStreamBeginCapture");
+    try {
+      runStep(x, t, global_bunch);
+    } catch (...) {
+      g_capture_registry = nullptr;
+      cudaGraph_t dead = nullptr;
+      cudaStreamEndCapture(stream, &dead);
+      if (dead) cudaGraphDestroy(dead);
+      throw;
+    }
+    g_capture_registry = nullptr;
+    cudaCheck(cudaStreamEndCapture(stream, &g->graph), "cudaStreamEndCapture");
+    cudaCheck(cudaGraphInstantiate(&g->exec, g->graph, 0), "cudaGraphInstantiate");
+    b200_launch_count(ctx, &after);
+    g->launches = after - before;
+    b200_add_launches(ctx, (uint64_t)0 - g->launches);  // capture enqueued nothing yet
+    g->rows = last_loss_rows;
+    g->out = last_output;
+    g->x_ptr = x->data;
+    g->t_ptr = t->data;
+    cudaCheck(cudaGraphLaunch(g->exec, stream), "cudaGraphLaunch");
+    b200_add_launches(ctx, g->launches);
+    optimizer.count++;
+    return;
+  }
+  runStep(x, t, global_bunch);
+  if (g) g->warm++;
+  optimizer.count++;
+}
+
+void SupervisedTrainer::validateStepDevice(const MatrixPtr &x, const MatrixPtr &t) {
+  // supervised.lua:825-862
+  net->reset();
+  auto *last = dynamic_cast<ActivationFunctionANNComponent *>(net->lastComponent());
+  const bool fused_loss =
+      net->fuse && last && last->act == B200_ACT_LOG_SOFTMAX && loss.kind == LOSS_MULTI_CLASS_CROSS_ENTROPY;
+  MatrixPtr out, rows, nograd;
+  if (fused_loss) {
+    net->defer_last_actf = true;
+    MatrixPtr logits = net->doForward(x, false);
+    net->defer_last_actf = false;
+    loss.fusedLogSoftmaxMCCE(logits, t, out, rows, nograd);
+    last->input = logits;
+    last->output = out;
+    net->output = out;
+  } else {
+    out = net->doForward(x, false);
+    rows = loss.computeLoss(out, t);
+  }
+  loss.accumLoss(rows);
+  last_loss_rows = rows;
+  last_output = out;
+}
+
+MatrixPtr SupervisedTrainer::calculate(const MatrixPtr &x) {
+  net->reset();
+  return net->doForward(x, false);
+}
+
+static MatrixPtr stageView(b200_ctx *ctx, MatrixPtr &stage, int rows, int cols, int min_rows) {
+  const size_t need = (size_t)std::max(rows, min_rows) * cols;
+  if (!stage || stage->size() < need) stage = Matrix::create(ctx, std::vector<int>{(int)need});
+  return Matrix::view(stage, 0, std::vector<int>{rows, cols});
+}
+
+float SupervisedTrainer::trainStep(const float *x, const float *t, int bunch, float *loss_rows_out) {
+  const int in = (int)net->getInputSize(), out = (int)net->getOutputSize();
+  if (in <= 0 || out <= 0) throw Error(B200_ERR_NOT_BUILT, "Execute build method before call this method");
+  MatrixPtr sx = stageView(ctx, stage_x, bunch, in, bunch_size);
+  MatrixPtr st = stageView(ctx, stage_t, bunch, out, bunch_size);
+  sx->fromHost(x);
+  st->fromHost(t);
+  trainStepDevice(sx, st);
+  std::vector<float> rows(bunch);
+  last_loss_rows->toHost(rows.data());
+  if (loss_rows_out) memcpy(loss_rows_out, rows.data(), sizeof(float) * bunch);
+  float s = 0.0f;  // matSum(loss)/dim  (bind_loss_functions.lua.cc:71)
+  for (float v : rows) s += v;
+  return s / (float)bunch;
+}
+float SupervisedTrainer::validateStep(const float *x, const float *t, int bunch, float *loss_rows_out) {
+  const int in = (int)net->getInputSize(), out = (int)net->getOutputSize();
+  MatrixPtr sx = stageView(ctx, stage_x, bunch, in, bunch_size);
+  MatrixPtr st = stageView(ctx, stage_t, bunch, out, bunch_size);
+  sx->fromHost(x);
+  st->fromHost(t);
+  validateStepDevice(sx, st);
+  std::vector<float> rows(bunch);
+  last_loss_rows->toHost(rows.data());
+  if (loss_rows_out) memcpy(loss_rows_out, rows.data(), sizeof(float) * bunch);
+  float s = 0.0f;
+  for (float v : rows) s += v;
+  return s / (float)bunch;
+}
+
+void SupervisedTrainer::trainDataset(const float *x, const float *t, int n, const int *order, float *mean,
+                                     float *var) {
+  // supervised.lua:1149-1226: loss:reset(), iterate bunches in the given order (the shuffle is
+  // drawn by the caller's random object, trainable.lua:217-220), return loss:get_accum_loss()
+  const int in = (int)net->getInputSize(), out = (int)net->getOutputSize();
+  if (in <= 0 || out <= 0) throw Error(B200_ERR_NOT_BUILT, "Execute build method before call this method");
+  MatrixPtr dx = Matrix::create(ctx, std::vector<int>{n, in});
+  MatrixPtr dt = Matrix::create(ctx, std::vector<int>{n, out});
+  dx->fromHost(x);
+  dt->fromHost(t);
+  std::vector<int32_t> idx(n);
+  for (int i = 0; i < n; ++i) idx[i] = order ? order[i] : i;
+  void *p;
+  check(b200_malloc(ctx, &p, sizeof(int32_t) * (size_t)n));
+  int32_t *idx_dev = (int32_t *)p;
+  check(b200_memcpy_h2d(ctx, idx_dev, idx.data(), sizeof(int32_t) * (size_t)n));
+  loss.reset();
+  for (int k = 0; k < n; k += bunch_size) {
+    const int b = std::min(bunch_size, n - k);
+    MatrixPtr sx = stageView(ctx, stage_x, b, in, bunch_size);
+    MatrixPtr st = stageView(ctx, stage_t, b, out, bunch_size);
+    check(b200_gather_rows(ctx, b, in, dx->data, idx_dev + k, sx->data));
+    check(b200_gather_rows(ctx, b, out, dt->data, idx_dev + k, st->data));
+    trainStepDevice(sx, st);
+  }
+  loss.getAccumLoss(mean, var);  // also synchronises: idx / dataset buffers are idle afterwards
+  check(b200_free(ctx, idx_dev));
+}
+
+void SupervisedTrainer::validateDataset(const float *x, const float *t, int n, float *mean, float *var) {
+  const int in = (int)net->getInputSize(), out = (int)net->getOutputSize();
+  MatrixPtr dx = Matrix::create(ctx, std::vector<int>{n, in});
+  MatrixPtr dt = Matrix::create(ctx, std::vector<int>{n, out});
+  dx->fromHost(x);
+  dt->fromHost(t);
+  loss.reset();
+  for (int k = 0; k < n; k += bunch_size) {
+    const int b = std::min(bunch_size, n - k);
+    validateStepDevice(Matrix::view(dx, (size_t)k * in, std::vector<int>{b, in}),
+                       Matrix::view(dt, (size_t)k * out, std::vector<int>{b, out}));
+  }
+  loss.getAccumLoss(mean, var);
+}
+
+double SupervisedTrainer::norm2(const std::string &pattern) {
+  // supervised.lua:1556-1576: max over matching matrices of the largest row 2-norm
+  double best = 0.0;
+  for (auto &n : weights_order) {
+    if (!luaPatternMatch(pattern, n)) continue;
+    MatrixPtr w = weights_table[n];
+    std::vector<float> h(w->size());
+    w->toHost(h.data());
+    const int rows = w->dim(0), cols = w->cols();
+    for (int r = 0; r < rows; ++r) {
+      double s = 0;
+      for (int c = 0; c < cols; ++c) s += (double)h[(size_t)r * cols + c] * h[(size_t)r * cols + c];
+      best = std::max(best, sqrt(s));
+    }
+  }
+  return best;
+}
+
+void SupervisedTrainer::broadcastWeights() {
+  check(b200_broadcast(ctx, weights_arena->data, weights_arena->size(), 0));
+  check(b200_sync(ctx));
+}
+
+}  // namespace b200
+
+namespace b200 {
+// pipelined stepping used by train loops that keep the loss on the device
+void SupervisedTrainer::stage(const float *x, const float *t, int bunch) {
+  const int in = (int)net->getInputSize(), out = (int)net->getOutputSize();
+  if (in <= 0 || out <= 0) throw Error(B200_ERR_NOT_BUILT, "Execute build method before call this method");
+  stageView(ctx, stage_x, bunch, in, bunch_size)->fromHost(x);
+  stageView(ctx, stage_t, bunch, out, bunch_size)->fromHost(t);
+}
+void SupervisedTrainer::stepStaged(int bunch) {
+  const int in = (int)net->getInputSize(), out = (int)net->getOutputSize();
+  if (!stage_x || !stage_t) throw Error(B200_ERR_BAD_ARG, "step_staged before stage");
+  trainStepDevice(stageView(ctx, stage_x, bunch, in, bunch_size), stageView(ctx, stage_t, bunch, out, bunch_size));
+}
+}  // namespace b200

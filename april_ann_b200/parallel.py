@@ -1,0 +1,48 @@
+"""Data-parallel plumbing: one process per GPU, a weight replica per rank, gradients summed
+with NCCL before the fused SGD update.  New relative to the reference (single device 0,
+mathcore/c_src/gpu_helper.h:65-68).  torch.distributed is used only for the rendezvous, the
+NCCL unique-id exchange and max-over-ranks timing; the collective on the data path is the
+library's own ncclAllReduce on the flat gradient arena (csrc/nccl_dp.cu).
+
+Semantics (kept equal to a single-device step on the concatenated bunch): every rank runs
+forward/backward on its rows of the global bunch; raw gradients are sums over rows, so the sum
+over ranks is the global sum; the reference's smoothing factor 1/sqrt(shared_count * bunch)
+(packages/trainable/lua_src/supervised.lua:797-803) uses the GLOBAL bunch size.
+"""
+import ctypes as C
+import math
+
+from ._lib import lib, check
+
+
+def shard_rows(n, rank, world):
+    """Row range [lo, hi) of a global bunch of n rows owned by `rank` (contiguous, balanced)."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def dp_grad_scale(shared_count, global_bunch):
+    """The reference's gradient smoothing with the global bunch size."""
+    return 1.0 / math.sqrt(max(shared_count, 1) * global_bunch)
+
+
+def exchange_unique_id(dist):
+    """rank 0 creates the ncclUniqueId; everybody receives the 128 bytes."""
+    buf = (C.c_char * 128)()
+    if dist.get_rank() == 0:
+        check(lib.b200_comm_unique_id(buf))
+    obj = [bytes(buf)]
+    dist.broadcast_object_list(obj, src=0)
+    return obj[0]
+
+
+def init_data_parallel(trainer, dist):
+    """Creates the NCCL communicator of the trainer's context, makes the trainer scale gradients
+    by the global bunch and all-reduce them, and broadcasts rank 0's weights to every replica."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    uid = exchange_unique_id(dist)
+    check(lib.b200_comm_init(trainer.ctx.h, C.c_int(world), C.c_int(rank), uid))
+    trainer.set_data_parallel(world, rank)
+    trainer.broadcast_weights()
+    dist.barrier()

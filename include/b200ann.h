@@ -1,0 +1,218 @@
+/*
+ * b200ann.h -- C ABI of the B200-native training hot path behind the APRIL-ANN API.
+ *
+ * Plain C: raw device pointers, int dims / leading dimensions, an explicit
+ * per-device context.  No C++ or torch types cross this boundary.  All matrices
+ * are float32, row-major.  Every entry point returns 0 on success and a non-zero
+ * status otherwise; b200_last_error_string() describes the last failure of the
+ * calling thread (the reference aborts through ERROR_EXIT,
+ * packages/basics/util/c_src/error_print.h:55-77; a host shim turns a non-zero
+ * status into that).  Kernels are enqueued on the context's stream and are
+ * asynchronous; b200_sync() waits.
+ *
+ * Each group cites the reference interface it replaces (paths relative to the
+ * reference checkout).
+ */
+#ifndef B200ANN_H
+#define B200ANN_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200_ctx b200_ctx;
+
+/* status codes (the reference's exit codes 150-163 are CUDA init/alloc/copy:
+ * packages/basics/mathcore/c_src/gpu_helper.h:57-68) */
+enum {
+  B200_OK = 0,
+  B200_ERR_BAD_ARG = 128,      /* same code the reference uses for bad sizes/types */
+  B200_ERR_NOT_BUILT = 129,
+  B200_ERR_CUDA = 150,
+  B200_ERR_ALLOC = 151,
+  B200_ERR_NCCL = 160,
+  B200_ERR_UNSUPPORTED = 161
+};
+
+/* activation kinds (packages/ann/ann/c_src/*_actf_component.cc) */
+enum {
+  B200_ACT_NONE = 0,
+  B200_ACT_LOGISTIC = 1,   /* 1/(1+e^-x);   derivative from output y(1-y), clamped */
+  B200_ACT_TANH = 2,       /* 2/(1+e^-x)-1; derivative from output 0.5(1-y^2), clamped */
+  B200_ACT_RELU = 3,       /* derivative (x>0), evaluated as (y>0) */
+  B200_ACT_SOFTMAX = 4,
+  B200_ACT_LOG_SOFTMAX = 5,
+  B200_ACT_LINEAR = 6
+};
+
+/* math modes for the contractions */
+enum {
+  B200_MATH_FP32 = 0,      /* FFMA fp32 accumulate: the parity mode (tolerance 1e-5 rel-L2) */
+  B200_MATH_TF32 = 1       /* tcgen05 kind::tf32, fp32 accumulate in TMEM (tolerance 2e-3 rel-L2) */
+};
+
+/* ------------------------------------------------------------------ runtime
+ * replaces GPUHelper (packages/basics/mathcore/c_src/gpu_helper.h:42-148) and the
+ * device half of GPUMirroredMemoryBlock
+ * (packages/basics/mathcore/c_src/gpu_mirrored_memory_block.h:178-304,476,518). */
+const char *b200_last_error_string(void);
+int b200_device_count(int *count);
+int b200_create(int device, b200_ctx **out);
+int b200_destroy(b200_ctx *ctx);
+int b200_set_math_mode(b200_ctx *ctx, int mode);
+int b200_get_math_mode(b200_ctx *ctx, int *mode);
+int b200_sm_count(b200_ctx *ctx, int *count);
+void *b200_stream(b200_ctx *ctx);                 /* cudaStream_t of the compute stream */
+int b200_sync(b200_ctx *ctx);
+int b200_malloc(b200_ctx *ctx, void **dptr, size_t bytes);   /* stream-ordered caching pool */
+int b200_free(b200_ctx *ctx, void *dptr);
+int b200_pool_trim(b200_ctx *ctx);                            /* return cached blocks to the driver */
+int b200_host_alloc(void **hptr, size_t bytes);               /* pinned host memory */
+int b200_host_free(void *hptr);
+int b200_memcpy_h2d(b200_ctx *ctx, void *dst, const void *src, size_t bytes);  /* async on the stream */
+int b200_memcpy_d2h(b200_ctx *ctx, void *dst, const void *src, size_t bytes);  /* async on the stream */
+int b200_memcpy_d2d(b200_ctx *ctx, void *dst, const void *src, size_t bytes);
+int b200_memset_zero(b200_ctx *ctx, void *dst, size_t bytes);
+/* CUDA-event timing on the compute stream (bench / roofline) */
+int b200_event_create(void **ev);
+int b200_event_destroy(void *ev);
+int b200_event_record(b200_ctx *ctx, void *ev);
+int b200_event_elapsed_ms(void *start, void *stop, float *ms);   /* synchronises on stop */
+/* number of kernels this library launched on ctx since creation (bench "gpu_launches") */
+int b200_launch_count(b200_ctx *ctx, uint64_t *count);
+
+/* ------------------------------------------------------------------ BLAS seam
+ * replaces AprilMath::doGemm/doGemv/doGer/doAxpy/doScal/doCopy
+ * (packages/basics/mathcore/c_src/cblas_headers.h:240-535, gemm.cu:248-327,
+ * gemv.cu:44, ger.cu:42, axpy.cu:42, scal.cu:38, copy.cu:43).
+ * Row-major; trans = 0 (no transpose) or 1 (transpose), as CblasNoTrans/CblasTrans. */
+int b200_sgemm(b200_ctx *ctx, int transA, int transB, int M, int N, int K,
+               float alpha, const float *A, int lda, const float *B, int ldb,
+               float beta, float *C, int ldc);
+int b200_sgemv(b200_ctx *ctx, int transA, int M, int N, float alpha, const float *A, int lda,
+               const float *x, int incx, float beta, float *y, int incy);
+int b200_sger(b200_ctx *ctx, int M, int N, float alpha, const float *x, int incx,
+              const float *y, int incy, float *A, int lda);
+int b200_saxpy(b200_ctx *ctx, size_t n, float alpha, const float *x, float *y);
+int b200_sscal(b200_ctx *ctx, size_t n, float alpha, float *x);
+int b200_scopy(b200_ctx *ctx, size_t n, const float *x, float *y);
+int b200_cmul(b200_ctx *ctx, size_t n, const float *x, float *y);          /* y *= x  (matCmul) */
+int b200_sum(b200_ctx *ctx, size_t n, const float *x, float *out);         /* *out = sum x (device scalar) */
+int b200_nrm2sq(b200_ctx *ctx, size_t n, const float *x, float *out);      /* *out += sum x^2 (device scalar) */
+
+/* ------------------------------------------------------------------ fused dense layer
+ * replaces DotProductANNComponent + BiasANNComponent + ActivationFunctionANNComponent
+ * (packages/ann/ann/c_src/dot_product_component.cc:63-98,123-152,194-216;
+ *  bias_component.cc:46-73,87-122; activation_function_component.cc:48-120).
+ *   fwd : Y[M,N]  = act( X[M,K] . W[N,K]^T + b[N] )                    (bias may be NULL)
+ *   bwd_data : dX[M,K] = ( dY[M,N] . W[N,K] ) (.) act'(Yprev[M,K])      (act_prev NONE => plain)
+ *              where Yprev is the OUTPUT of the previous activation
+ *   bwd_weight : dW[N,K] = beta*dW + scale * dY[M,N]^T . X[M,K]
+ *                db[N]   = beta*db + scale * sum_m dY[m,:]              (db may be NULL)
+ *   scale carries the trainer's 1/sqrt(shared_count*bunch)
+ *   (packages/trainable/lua_src/supervised.lua:797-803). */
+int b200_linear_fwd(b200_ctx *ctx, int M, int N, int K, const float *X, int ldx,
+                    const float *W, int ldw, const float *bias, int act, float *Y, int ldy);
+int b200_linear_bwd_data(b200_ctx *ctx, int M, int N, int K, const float *dY, int lddy,
+                         const float *W, int ldw, int act_prev, const float *Yprev, int ldyp,
+                         float *dX, int lddx);
+int b200_linear_bwd_weight(b200_ctx *ctx, int M, int N, int K, const float *dY, int lddy,
+                           const float *X, int ldx, float scale, float beta,
+                           float *dW, int lddw, float *db);
+
+/* ------------------------------------------------------------------ element-wise
+ * replaces ANN::Kernels::apply* (packages/ann/ann/c_src/activation_function_kernels.cu:60-182)
+ * and the bias axpy loops (mathcore/c_src/axpy.cu:111,275). */
+int b200_actf_fwd(b200_ctx *ctx, int act, size_t n, const float *x, float *y);
+/* dx = act'(.) * dy ; y = activation output (relu: y>0 <=> x>0) */
+int b200_actf_bwd(b200_ctx *ctx, int act, size_t n, const float *y, const float *dy, float *dx);
+int b200_bias_fwd(b200_ctx *ctx, int M, int N, const float *x, const float *b, float *y);
+int b200_bias_grad(b200_ctx *ctx, int M, int N, const float *dy, int lddy, float scale,
+                   float beta, float *db);
+
+/* ------------------------------------------------------------------ row-wise
+ * replaces applySoftmax/applyLogSoftmax/applySoftmaxDerivative
+ * (activation_function_kernels.cu:184-355) and the loss kernels
+ * (packages/ann/loss/c_src/loss_kernels.cu:38-266, multiclass_cross_entropy_loss_function.cc:48-71,
+ *  mse_loss_function.cc:41-109, cross_entropy_loss_function.cc:41-118). */
+int b200_softmax_fwd(b200_ctx *ctx, int M, int C, const float *x, float *y);
+int b200_log_softmax_fwd(b200_ctx *ctx, int M, int C, const float *x, float *y);
+int b200_softmax_bwd(b200_ctx *ctx, int M, int C, const float *y, const float *dy, float *dx);
+/* loss_rows[M] and/or grad[M,C] (either may be NULL) */
+int b200_mcce_loss_grad(b200_ctx *ctx, int M, int C, const float *logp, const float *target,
+                        float *loss_rows, float *grad);
+int b200_mse_loss_grad(b200_ctx *ctx, int M, int C, const float *out, const float *target,
+                       float *loss_rows, float *grad);
+int b200_ce_loss_grad(b200_ctx *ctx, int M, int C, const float *log_out, const float *target,
+                      float *loss_rows, float *grad);
+/* one pass: logits -> logp (may be NULL), loss_rows, grad = exp(clamp(logp)) - target */
+int b200_log_softmax_mcce_fused(b200_ctx *ctx, int M, int C, const float *logits,
+                                const float *target, float *logp, float *loss_rows, float *grad);
+/* running statistics over loss rows on the device:
+ * stats[0] += sum(rows), stats[1] += sum(rows^2), stats[2] += M   (float64 on the device) */
+int b200_loss_accumulate(b200_ctx *ctx, int M, const float *loss_rows, double *stats);
+
+/* ------------------------------------------------------------------ SGD
+ * replaces ann.optimizer.sgd:execute (packages/ann/optimizer/lua_src/optimizer_sgd.lua:50-100)
+ * and its helpers (base_optimizer.lua:28-49).  One launch updates every tensor:
+ *   g += l2*w ; u = mt*u (or 0) ; u += lrd*g ; w -= u ; [L1 truncate] ; [prune subnormals]
+ * with lrd = lr / (1 + decay*count) computed on the device from *count (int64, device). */
+typedef struct {
+  float *w;              /* weights, updated in place            */
+  float *g;              /* gradients (already scaled)           */
+  float *u;              /* momentum/update buffer               */
+  uint64_t n;            /* elements                             */
+  int32_t rows, cols;    /* for max_norm_penalty (rows of w)     */
+  float lr, momentum, weight_decay, l1_norm, max_norm_penalty;
+  int32_t pad_;
+} b200_sgd_tensor;
+int b200_sgd_multi_tensor(b200_ctx *ctx, int ntensors, const b200_sgd_tensor *tensors_dev,
+                          const b200_sgd_tensor *tensors_host, double decay,
+                          const int64_t *count_dev, int write_back_grad);
+int b200_counter_increment(b200_ctx *ctx, int64_t *count_dev);
+
+/* ------------------------------------------------------------------ convolution / pooling
+ * replaces ConvolutionANNComponent, ConvolutionBiasANNComponent, MaxPoolingANNComponent
+ * (packages/ann/ann/c_src/convolution_component.cc:135-354, convolution_bias_component.cc:120-222,
+ *  maxpooling_component.cc:129-260).  NCHW, valid convolution, W[n, C*kh*kw] flattened in
+ *  (plane,row,col) order. */
+int b200_conv2d_fwd(b200_ctx *ctx, int B, int C, int H, int W_, int n, int kh, int kw, int sh, int sw,
+                    const float *x, const float *w, const float *bias, int act, float *y);
+int b200_conv2d_bwd_data(b200_ctx *ctx, int B, int C, int H, int W_, int n, int kh, int kw, int sh,
+                         int sw, const float *dy, const float *w, float *dx);
+int b200_conv2d_bwd_weight(b200_ctx *ctx, int B, int C, int H, int W_, int n, int kh, int kw, int sh,
+                           int sw, const float *dy, const float *x, float scale, float beta,
+                           float *dw, float *db);
+/* y[b,p,:] = x[b,p,:] + bias[p] ; db[p] = beta*db[p] + scale * sum_{b,pixels} dy[b,p,:] */
+int b200_conv_bias_fwd(b200_ctx *ctx, int B, int n, int HW, const float *x, const float *bias, float *y);
+int b200_conv_bias_grad(b200_ctx *ctx, int B, int n, int HW, const float *dy, float scale, float beta,
+                        float *db);
+int b200_maxpool_fwd(b200_ctx *ctx, int B, int C, int H, int W_, int kh, int kw, int sh, int sw,
+                     const float *x, float *y, int32_t *argmax);
+int b200_maxpool_bwd(b200_ctx *ctx, int B, int C, int H, int W_, int kh, int kw, int sh, int sw,
+                     const float *dy, const int32_t *argmax, float *dx);
+
+/* ------------------------------------------------------------------ input staging
+ * replaces DataSetToken::getPatternBunch (packages/basics/dataset/c_src/datasetToken.h:182-209):
+ * out[i,:] = data[idx[i],:] on the device. */
+int b200_gather_rows(b200_ctx *ctx, int nrows, int cols, const float *data, const int32_t *idx,
+                     float *out);
+
+/* ------------------------------------------------------------------ data parallel
+ * new (the reference has no multi-GPU path: gpu_helper.h:65-68 hard-codes device 0).
+ * NCCL communicator per context; id is ncclUniqueId bytes from rank 0. */
+int b200_comm_unique_id(void *id128);                             /* 128 bytes out */
+int b200_comm_init(b200_ctx *ctx, int nranks, int rank, const void *id128);
+int b200_comm_destroy(b200_ctx *ctx);
+int b200_allreduce_sum(b200_ctx *ctx, float *buf, size_t n);      /* in place, on the comm stream,
+                                                                     ordered after/before the compute stream */
+int b200_allreduce_sum_f64(b200_ctx *ctx, double *buf, size_t n);
+int b200_broadcast(b200_ctx *ctx, float *buf, size_t n, int root);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200ANN_H */

@@ -1,0 +1,108 @@
+/*
+ * b200ann_host.h -- C ABI of the host-side mirror (components, losses, SGD, trainer,
+ * random) that language bindings attach to.  These are the calls the reference's Lua
+ * binding layer makes on its C++ objects:
+ *   ann.components.*              packages/ann/ann/binding/bind_ann_base.lua.cc:287-2187
+ *   ann.loss.*                    packages/ann/loss/binding/bind_loss_functions.lua.cc:50-140
+ *   ann.mlp.all_all.generate      packages/ann/ann/lua_src/annbase.lua:509-660
+ *   trainable.supervised_trainer  packages/trainable/lua_src/supervised.lua
+ *   ann.optimizer.sgd options     packages/ann/optimizer/lua_src/optimizer_sgd.lua:22-48
+ *   random                        packages/basics/random/binding/bind_mtrand.lua.cc
+ * Opaque handles, plain C types, int status (0 = ok; b200_last_error_string() explains).
+ * Host float buffers are row-major float32.
+ */
+#ifndef B200ANN_HOST_H
+#define B200ANN_HOST_H
+
+#include "b200ann.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200_component b200_component;
+typedef struct b200_trainer b200_trainer;
+typedef struct b200_random b200_random;
+
+enum { B200_LOSS_MSE = 0, B200_LOSS_CROSS_ENTROPY = 1, B200_LOSS_MULTI_CLASS_CROSS_ENTROPY = 2 };
+enum { B200_TOKEN_INPUT = 0, B200_TOKEN_OUTPUT = 1, B200_TOKEN_ERROR_INPUT = 2, B200_TOKEN_ERROR_OUTPUT = 3 };
+
+int b200_add_launches(b200_ctx *ctx, uint64_t n);   /* graph replays: kernels launched per replay */
+
+/* random(seed) -- bind_mtrand.lua.cc:45-75,85-166,168-215 */
+b200_random *b200h_random_new(uint32_t seed);
+void b200h_random_free(b200_random *r);
+double b200h_random_rand(b200_random *r, double n);
+uint32_t b200h_random_randint(b200_random *r, uint32_t n);     /* [0, n] */
+int b200h_random_shuffle(b200_random *r, int size, int *out);   /* 0-based permutation */
+
+/* component constructors (ownership: the caller frees its handle; stacks share ownership) */
+b200_component *b200h_stack_new(const char *name);
+int b200h_stack_push(b200_component *stack, b200_component *child);
+b200_component *b200h_hyperplane_new(const char *name, unsigned in, unsigned out, const char *dot_name,
+                                     const char *bias_name, const char *dot_weights, const char *bias_weights);
+b200_component *b200h_dot_product_new(const char *name, const char *weights, unsigned in, unsigned out);
+b200_component *b200h_bias_new(const char *name, const char *weights, unsigned size);
+b200_component *b200h_actf_new(const char *kind, const char *name);
+b200_component *b200h_rewrap_new(const char *name, const int *size, int ndims);
+b200_component *b200h_flatten_new(const char *name);
+b200_component *b200h_convolution_new(const char *name, const char *weights, const int *kernel, const int *step,
+                                      int ndims, int n);
+b200_component *b200h_convolution_bias_new(const char *name, const char *weights, int n);
+b200_component *b200h_max_pooling_new(const char *name, const int *kernel, const int *step, int ndims);
+b200_component *b200h_mlp_generate(const char *topology);
+void b200h_component_free(b200_component *c);
+
+/* trainable.supervised_trainer(component, loss, bunch_size) */
+b200_trainer *b200h_trainer_new(b200_ctx *ctx, b200_component *net, int loss_kind, int bunch_size);
+void b200h_trainer_free(b200_trainer *t);
+int b200h_trainer_build(b200_trainer *t, unsigned input, unsigned output);
+int b200h_trainer_set_option(b200_trainer *t, const char *name, double value);
+int b200h_trainer_get_option(b200_trainer *t, const char *name, double *value);
+int b200h_trainer_set_layerwise_option(b200_trainer *t, const char *pattern, const char *name, double value);
+int b200h_trainer_randomize_weights(b200_trainer *t, b200_random *rnd, double inf, double sup, int use_fanin,
+                                    int use_fanout, const char *name_match /* may be NULL */);
+/* flags: "fuse", "cuda_graph", "keep_gradients", "smooth_gradients" */
+int b200h_trainer_set_flag(b200_trainer *t, const char *flag, int value);
+int b200h_trainer_num_weights(b200_trainer *t, int *n);
+int b200h_trainer_weight_name(b200_trainer *t, int i, char *buf, int buflen);
+int b200h_trainer_weight_dims(b200_trainer *t, const char *name, int *dims2);
+/* which: 0 weights, 1 gradients (of the last step), 2 momentum/update buffer */
+int b200h_trainer_tensor_get(b200_trainer *t, const char *name, int which, float *host);
+int b200h_trainer_tensor_set(b200_trainer *t, const char *name, int which, const float *host);
+int b200h_trainer_num_parameters(b200_trainer *t, uint64_t *n);
+int b200h_trainer_input_size(b200_trainer *t, int *n);
+int b200h_trainer_output_size(b200_trainer *t, int *n);
+
+/* train_step / validate_step (supervised.lua:725-862): host bunch in, bunch-mean loss out */
+int b200h_trainer_train_step(b200_trainer *t, const float *x, const float *target, int bunch, float *loss,
+                             float *loss_rows /* may be NULL */);
+int b200h_trainer_validate_step(b200_trainer *t, const float *x, const float *target, int bunch, float *loss,
+                                float *loss_rows);
+/* train_dataset / validate_dataset (supervised.lua:1149-1226,1291-1360): order = shuffled pattern
+ * indices (0-based) or NULL for sequential; returns loss:get_accum_loss() */
+int b200h_trainer_train_dataset(b200_trainer *t, const float *x, const float *target, int n, const int *order,
+                                float *mean, float *variance);
+int b200h_trainer_validate_dataset(b200_trainer *t, const float *x, const float *target, int n, float *mean,
+                                   float *variance);
+/* calculate (forward only): y must hold bunch*output_size floats */
+int b200h_trainer_calculate(b200_trainer *t, const float *x, int bunch, float *y);
+/* token of a named component after the last step: dims[4], data may be NULL to query the shape;
+ * returns B200_ERR_BAD_ARG if the token was not materialised (inside a fused run) */
+int b200h_trainer_component_token(b200_trainer *t, const char *component, int which, float *data, int *dims,
+                                  int *ndims);
+/* pipelined stepping: enqueue H2D of a bunch into the staging buffers / run a step on them
+ * without any device->host traffic / read the accumulated loss statistics */
+int b200h_trainer_stage(b200_trainer *t, const float *x_pinned, const float *target_pinned, int bunch);
+int b200h_trainer_step_staged(b200_trainer *t, int bunch);
+int b200h_trainer_loss_reset(b200_trainer *t);
+int b200h_trainer_loss_get(b200_trainer *t, float *mean, float *variance);
+int b200h_trainer_last_loss_async(b200_trainer *t, double *pinned_out);  /* enqueue D2H of the last bunch's loss sum */
+/* data parallel replica group */
+int b200h_trainer_set_data_parallel(b200_trainer *t, int nranks, int rank);
+int b200h_trainer_broadcast_weights(b200_trainer *t);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -636,10 +636,21 @@ class SupervisedTrainer:
             if abs(dsup) < 1e-7:
                 dsup = -1e-7
             rng = dsup - dinf
+            saved = (random.state.copy(), random._out.copy(), random._pos)
             vals = (random.rand_array(w.size, rng) + dinf).astype(f32)
-            bad = np.abs(vals) < 1e-7
-            if bad.any():  # re-draws consume extra numbers: fall back to the scalar loop
-                raise NotImplementedError("weightnearzero re-draw hit; scalar path needed")
+            if (np.abs(vals) < 1e-7).any():
+                # a near-zero weight is re-drawn (rnd_weight macro, connection.cc:37-46), which
+                # shifts every later draw: redo this tensor with the scalar loop
+                random.state, random._out, random._pos = saved
+                vals = np.empty(w.size, dtype=f32)
+                for i in range(w.size):
+                    it = 0
+                    while True:
+                        v = f32(random.rand(rng) + dinf)
+                        it += 1
+                        if not (it < 1000 and abs(v) < 1e-7):
+                            break
+                    vals[i] = v
             w[...] = vals.reshape(w.shape)
 
     # supervised.lua:725-821
