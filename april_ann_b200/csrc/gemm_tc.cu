@@ -227,7 +227,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         tmem_ld32(taddr + c0, r);
         if (m < p.M) {
           const int nbase = n0 + c0;
-          const bool full_vec = (nbase + 32 <= p.N) && ((p.ldc & 3) == 0) && ((nbase & 3) == 0) &&
+          const int n_end = min(p.N, n0 + p.BN);     // BN need not be a multiple of the 32-column chunk
+          const bool full_vec = (nbase + 32 <= n_end) && ((p.ldc & 3) == 0) && ((nbase & 3) == 0) &&
                                 ((((uintptr_t)p.C) & 15) == 0) && p.ep.beta == 0.0f && p.ep.dact == B200_ACT_NONE;
           if (full_vec) {
 #pragma unroll
@@ -243,7 +244,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               const int n = nbase + j;
-              if (n < p.N) {
+              if (n < n_end) {
                 const float cold = (p.ep.beta != 0.0f) ? crow[n] : 0.0f;
                 crow[n] = epilogue_apply(p.ep, __uint_as_float(r[j]), m, n, cold);
               }

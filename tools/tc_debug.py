@@ -37,8 +37,11 @@ def run_case(ta, tb, M, N, K, override=None, force_bn=0):
         M, N, K, ta, tb, err.max(), bad, err.size, ctx.launch_count() - n0), flush=True)
     if bad:
         r, c = np.argwhere(err > 1e-3)[0]
+        br, bc = np.unique(np.argwhere(err > 1e-3)[:, 0]), np.unique(np.argwhere(err > 1e-3)[:, 1])
         print("   first bad at (%d,%d): got %.3f want %.3f ; bad rows %s... bad cols %s..." % (
-            r, c, got[r, c], want[r, c], np.unique(np.argwhere(err > 1e-3)[:, 0])[:8], np.unique(np.argwhere(err > 1e-3)[:, 1])[:8]))
+            r, c, got[r, c], want[r, c], br[:8], bc[:8]))
+        print("   bad rows: n=%d min=%d max=%d ; bad cols: n=%d min=%d max=%d ; zero-valued among bad: %d" % (
+            len(br), br.min(), br.max(), len(bc), bc.min(), bc.max(), int((got[err > 1e-3] == 0).sum())))
     return bad == 0
 
 
@@ -46,6 +49,8 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "case":
         ta, tb, M, N, K = [int(v) for v in sys.argv[2:7]]
         ov = [int(v) for v in sys.argv[7:15]] if len(sys.argv) >= 15 else None
+        if ov is not None and not any(ov):
+            ov = None
         fbn = int(sys.argv[15]) if len(sys.argv) > 15 else 0
         ok = run_case(ta, tb, M, N, K, ov, fbn)
         sys.exit(0 if ok else 1)
