@@ -109,6 +109,17 @@ __device__ __forceinline__ float epilogue_apply(const GemmEpilogue &e, float acc
   return v;
 }
 
+// same, with the bias / derivative-source / old-C values already loaded (vectorised callers)
+__device__ __forceinline__ float epilogue_apply_v(const GemmEpilogue &e, float acc, float bias, float dsrc,
+                                                  float cold) {
+  float v = e.alpha * acc;
+  if (e.bias) v += bias;
+  if (e.act != B200_ACT_NONE) v = act_apply(e.act, v);
+  if (e.dact != B200_ACT_NONE) v *= act_deriv_from_output(e.dact, dsrc);
+  if (e.beta != 0.0f) v += e.beta * cold;
+  return v;
+}
+
 // internal entry points shared between translation units
 int gemm_simt(b200_ctx *ctx, int transA, int transB, int M, int N, int K, const float *A, int lda,
               const float *B, int ldb, float *C, int ldc, const GemmEpilogue &ep);

@@ -14,6 +14,7 @@
 // 128B-swizzle-with-32B-atoms layout (UMMA layout type 1, TMA SWIZZLE_128B_ATOM_32B), loaded as
 // 32(MN) x 32(K) boxes of 4 KiB each.
 #include <cuda.h>
+#include <math.h>
 
 #include <unordered_map>
 
@@ -24,12 +25,12 @@ namespace {
 constexpr int BM = 128;          // UMMA M (cta_group::1)
 constexpr int BK = 32;           // fp32 elements per 128-byte swizzle row
 constexpr int UMMA_K = 8;        // tf32: 32 bytes of K per instruction
-constexpr int STAGES = 4;
+constexpr int MAX_STAGES = 8;
 constexpr int MAX_BN = 256;
 constexpr int A_BYTES = BM * BK * 4;          // 16 KiB
-constexpr int B_BYTES = MAX_BN * BK * 4;      // 32 KiB
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int STAGING_BYTES = 4 * 2 * 32 * 32 * 4;   // two 32x32 fp32 staging buffers per epilogue warp
+constexpr int SMEM_EXTRA = STAGING_BYTES + 256 /*barriers*/ + 1024 /*align slack*/;
+constexpr int SMEM_MAX = 227 * 1024;
 constexpr int NTHREADS = 192;
 constexpr int TMEM_COLS = 512;   // two 256-column accumulator stages
 
@@ -63,6 +64,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
       "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0),
+               "r"(c1)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t cols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(cols) : "memory");
@@ -111,6 +118,8 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 struct TcParams {
   int M, N, K;
   int BN;            // N tile (multiple of 16, <= 256)
+  int stages;        // smem ring depth (<= MAX_STAGES)
+  uint32_t stage_bytes;   // A_BYTES + B tile bytes (multiple of 1 KiB)
   int ldc;
   float *C;
   GemmEpilogue ep;
@@ -118,22 +127,148 @@ struct TcParams {
   uint32_t a_lbo, a_sbo, a_layout, a_kstep;
   uint32_t b_lbo, b_sbo, b_layout, b_kstep;
   uint32_t idesc;
+  int tma_store;       // 1: the epilogue writes C through map_c (cp.async.bulk.tensor store), 0: direct stores
+  uint32_t dbg_flags;  // bring-up only: 8 = force direct stores instead of TMA stores
+  long long *stamps;   // bring-up only: per-CTA clock64 stamps [grid][8] (nullptr in production)
 };
+
+// v = alpha*acc (+ bias) ; v = ACT(v) ; v *= DACT'(dsrc) ; v += beta*cold  -- ACT / DACT fixed at compile time
+template <int ACT, int DACT>
+__device__ __forceinline__ float epi_value(const GemmEpilogue &e, bool has_bias, bool has_c, float acc, float bias,
+                                           float dsrc, float cold) {
+  float v = e.alpha * acc;
+  if (has_bias) v += bias;
+  if (ACT != B200_ACT_NONE) v = act_apply(ACT, v);
+  if (DACT != B200_ACT_NONE) v *= act_deriv_from_output(DACT, dsrc);
+  if (has_c) v = fmaf(e.beta, cold, v);
+  return v;
+}
+
+// Epilogue of one 128 x BN accumulator for one warp (32 TMEM lanes = 32 rows starting at m_base):
+// tcgen05.ld 32 columns at a time -> shared memory (transpose) -> global through a TMA store, or
+// direct row-contiguous stores when C cannot be described by a tensor map.
+template <int ACT, int DACT>
+__device__ __noinline__ void epilogue_tile(const TcParams &p, const CUtensorMap *map_c, uint32_t taddr, uint32_t stg,
+                                           int m_base, int n0, int lane, int &chunk) {
+  const int n_end = min(p.N, n0 + p.BN);
+  const int cg = lane & 7;                       // 16-byte column group this lane handles after the transpose
+  const bool has_bias = p.ep.bias != nullptr, has_c = p.ep.beta != 0.0f;
+  constexpr bool has_d = DACT != B200_ACT_NONE;
+  const bool c_vec = ((p.ldc & 3) == 0) && ((((uintptr_t)p.C) & 15) == 0);
+  const bool d_vec = !has_d || (((p.ep.ld_dsrc & 3) == 0) && ((((uintptr_t)p.ep.dsrc) & 15) == 0));
+  // simple epilogues (alpha, bias, activation) are applied in the accumulator layout (lane = row);
+  // the ones that read global memory per element (derivative source, old C) run after the transpose
+  const bool simple = p.tma_store && !has_d && !has_c;
+  for (int c0 = 0; c0 < p.BN; c0 += 32, ++chunk) {
+    const uint32_t buf = stg + (uint32_t)(chunk & 1) * 4096u;
+    if (p.tma_store) {
+      // the bulk store that last read this buffer (two chunks ago) must have finished reading it
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      __syncwarp();
+    }
+    uint32_t r[32];
+    tmem_ld32(taddr + c0, r);                    // lane = accumulator row, 32 consecutive columns
+    if (n0 + c0 >= n_end) break;
+    if (simple) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int n = n0 + c0 + j;
+        const float b = (has_bias && n < n_end) ? __ldg(p.ep.bias + n) : 0.0f;
+        r[j] = __float_as_uint(epi_value<ACT, DACT>(p.ep, has_bias, false, __uint_as_float(r[j]), b, 1.0f, 0.0f));
+      }
+    }
+    // 32x32 tile -> shared memory, 16-byte groups XOR-swizzled by the row (= TMA SWIZZLE_128B, and
+    // conflict-free for the row-wise reads below)
+#pragma unroll
+    for (int g = 0; g < 8; ++g)
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(buf + (uint32_t)lane * 128u + (uint32_t)((g ^ (lane & 7)) << 4)),
+                   "r"(r[4 * g]), "r"(r[4 * g + 1]), "r"(r[4 * g + 2]), "r"(r[4 * g + 3]) : "memory");
+    if (!simple) {
+      __syncwarp();
+      // row-contiguous domain: 8 lanes cover the 128 bytes of one row, global accesses coalesce
+      const int n = n0 + c0 + 4 * cg;
+      float bv[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+      if (has_bias) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (n + e < n_end) bv[e] = __ldg(p.ep.bias + n + e);
+      }
+#pragma unroll 2
+      for (int it = 0; it < 8; ++it) {
+        const int row = it * 4 + (lane >> 3);
+        const uint32_t saddr = buf + (uint32_t)row * 128u + (uint32_t)((cg ^ (row & 7)) << 4);
+        float v[4];
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3])
+                     : "r"(saddr) : "memory");
+        const int m = m_base + row;
+        if (m >= p.M || n >= n_end) continue;
+        float *cp = p.C + (size_t)m * p.ldc + n;
+        const float *dp = p.ep.dsrc + (size_t)m * p.ep.ld_dsrc + n;
+        const bool full4 = n + 4 <= n_end;
+        float d[4] = {1.0f, 1.0f, 1.0f, 1.0f}, c[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        if (has_d) {
+          if (full4 && d_vec) {
+            const float4 t = __ldg(reinterpret_cast<const float4 *>(dp));
+            d[0] = t.x; d[1] = t.y; d[2] = t.z; d[3] = t.w;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (n + e < n_end) d[e] = __ldg(dp + e);
+          }
+        }
+        if (has_c) {
+          if (full4 && c_vec) {
+            const float4 t = *reinterpret_cast<const float4 *>(cp);
+            c[0] = t.x; c[1] = t.y; c[2] = t.z; c[3] = t.w;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (n + e < n_end) c[e] = cp[e];
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] = epi_value<ACT, DACT>(p.ep, has_bias, has_c, v[e], bv[e], d[e], c[e]);
+        if (p.tma_store) {
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+        } else if (full4 && c_vec) {
+          *reinterpret_cast<float4 *>(cp) = make_float4(v[0], v[1], v[2], v[3]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (n + e < n_end) cp[e] = v[e];
+        }
+      }
+    }
+    if (p.tma_store) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the TMA
+      __syncwarp();
+      if (lane == 0) tma_store_2d(map_c, buf, n0 + c0, m_base);      // rows/columns past M/N are clipped
+    } else {
+      __syncwarp();
+    }
+  }
+}
 
 template <bool A_KMAJOR, bool B_KMAJOR>
 __global__ void __launch_bounds__(NTHREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const __grid_constant__ CUtensorMap map_c, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1 KiB alignment
-  const uint32_t bars = smem_base + STAGES * STAGE_BYTES;
-  // barrier layout (8 bytes each): full[4] empty[4] tmem_full[2] tmem_empty[2] ; then the TMEM base slot
+  const int STAGES = p.stages;
+  const uint32_t STAGE_BYTES = p.stage_bytes;
+  const uint32_t staging = smem_base + STAGES * STAGE_BYTES;
+  const uint32_t bars = staging + STAGING_BYTES;
+  // barrier layout (8 bytes each): full[8] empty[8] tmem_full[2] tmem_empty[2] ; then the TMEM base slot
   auto full_bar = [&](int s) { return bars + 8 * s; };
-  auto empty_bar = [&](int s) { return bars + 8 * (STAGES + s); };
-  auto tfull_bar = [&](int a) { return bars + 8 * (2 * STAGES + a); };
-  auto tempty_bar = [&](int a) { return bars + 8 * (2 * STAGES + 2 + a); };
-  const uint32_t tmem_slot = bars + 8 * (2 * STAGES + 4);
+  auto empty_bar = [&](int s) { return bars + 8 * (MAX_STAGES + s); };
+  auto tfull_bar = [&](int a) { return bars + 8 * (2 * MAX_STAGES + a); };
+  auto tempty_bar = [&](int a) { return bars + 8 * (2 * MAX_STAGES + 2 + a); };
+  const uint32_t tmem_slot = bars + 8 * (2 * MAX_STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  long long *stamp = p.stamps ? p.stamps + 8 * blockIdx.x : nullptr;
+  if (stamp && threadIdx.x == 0) stamp[0] = clock64();
   const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + p.BN - 1) / p.BN;
   const int num_tiles = tiles_m * tiles_n;
   const int num_k = (p.K + BK - 1) / BK;
@@ -144,6 +279,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    if (p.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c) : "memory");
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
   tc_fence_before();
@@ -151,12 +287,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  if (stamp && threadIdx.x == 0) stamp[1] = clock64();
 
   if (warp == 0) {
     // ================================ TMA producer ================================
     if (lane == 0) {
       // TMA always writes (and signals) whole boxes, also when they are partly out of bounds
       const uint32_t stage_tx = (uint32_t)A_BYTES + (B_KMAJOR ? (uint32_t)p.BN * BK * 4 : (uint32_t)((p.BN + 31) / 32) * 4096u);
+      (void)staging;
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -177,6 +315,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           } else {
             for (int j = 0; j < (p.BN + 31) / 32; ++j) tma_load_2d(sb + j * 4096, &map_b, full_bar(stage), n0 + 32 * j, k0);
           }
+          if (stamp && kb == 0 && tile == (int)blockIdx.x) stamp[2] = clock64();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -196,6 +335,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
+          if (stamp && kb == 0 && local == 0) stamp[3] = clock64();
           const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
@@ -207,59 +347,50 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(tfull_bar(acc));                 // accumulator complete -> epilogue
+        if (stamp) stamp[4] = clock64();
       }
     }
   } else {
     // ================================ epilogue warps ==============================
     const int quad = warp & 3;                        // TMEM lanes [32*quad, 32*quad+32)
     int local = 0;
+    int chunk = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
       const int acc = local & 1;
       const uint32_t acc_phase = (uint32_t)(local >> 1) & 1;
       const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * p.BN;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const int m = m0 + quad * 32 + lane;
+      if (stamp && threadIdx.x == 64) stamp[5] = clock64();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * MAX_BN;
-      float *crow = p.C + (size_t)m * p.ldc;
-      for (int c0 = 0; c0 < p.BN; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(taddr + c0, r);
-        if (m < p.M) {
-          const int nbase = n0 + c0;
-          const int n_end = min(p.N, n0 + p.BN);     // BN need not be a multiple of the 32-column chunk
-          const bool full_vec = (nbase + 32 <= n_end) && ((p.ldc & 3) == 0) && ((nbase & 3) == 0) &&
-                                ((((uintptr_t)p.C) & 15) == 0) && p.ep.beta == 0.0f && p.ep.dact == B200_ACT_NONE;
-          if (full_vec) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 v;
-              v.x = epilogue_apply(p.ep, __uint_as_float(r[j + 0]), m, nbase + j + 0, 0.0f);
-              v.y = epilogue_apply(p.ep, __uint_as_float(r[j + 1]), m, nbase + j + 1, 0.0f);
-              v.z = epilogue_apply(p.ep, __uint_as_float(r[j + 2]), m, nbase + j + 2, 0.0f);
-              v.w = epilogue_apply(p.ep, __uint_as_float(r[j + 3]), m, nbase + j + 3, 0.0f);
-              *reinterpret_cast<float4 *>(crow + nbase + j) = v;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int n = nbase + j;
-              if (n < n_end) {
-                const float cold = (p.ep.beta != 0.0f) ? crow[n] : 0.0f;
-                crow[n] = epilogue_apply(p.ep, __uint_as_float(r[j]), m, n, cold);
-              }
-            }
-          }
+      const uint32_t stg = staging + (uint32_t)(warp - 2) * 8192u;
+      // the activation / derivative kind is a compile-time constant inside each instantiation: a run-time
+      // switch per element made the unrolled epilogue ~4500 instructions per 32-column chunk
+      if (p.ep.dact != B200_ACT_NONE) {
+        switch (p.ep.dact) {
+          case B200_ACT_LOGISTIC: epilogue_tile<B200_ACT_NONE, B200_ACT_LOGISTIC>(p, &map_c, taddr, stg, m0 + quad * 32, n0, lane, chunk); break;
+          case B200_ACT_TANH: epilogue_tile<B200_ACT_NONE, B200_ACT_TANH>(p, &map_c, taddr, stg, m0 + quad * 32, n0, lane, chunk); break;
+          default: epilogue_tile<B200_ACT_NONE, B200_ACT_RELU>(p, &map_c, taddr, stg, m0 + quad * 32, n0, lane, chunk); break;
+        }
+      } else {
+        switch (p.ep.act) {
+          case B200_ACT_LOGISTIC: epilogue_tile<B200_ACT_LOGISTIC, B200_ACT_NONE>(p, &map_c, taddr, stg, m0 + quad * 32, n0, lane, chunk); break;
+          case B200_ACT_TANH: epilogue_tile<B200_ACT_TANH, B200_ACT_NONE>(p, &map_c, taddr, stg, m0 + quad * 32, n0, lane, chunk); break;
+          case B200_ACT_RELU: epilogue_tile<B200_ACT_RELU, B200_ACT_NONE>(p, &map_c, taddr, stg, m0 + quad * 32, n0, lane, chunk); break;
+          default: epilogue_tile<B200_ACT_NONE, B200_ACT_NONE>(p, &map_c, taddr, stg, m0 + quad * 32, n0, lane, chunk); break;
         }
       }
       tc_fence_before();
       mbar_arrive(tempty_bar(acc));
+      if (stamp && threadIdx.x == 64) stamp[6] = clock64();
     }
+    if (p.tma_store && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+  if (stamp && threadIdx.x == 0) stamp[7] = clock64();
 }
 
 // ------------------------------------------------------------------ host side
@@ -291,6 +422,9 @@ struct TcState {
   uint32_t dbg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   bool dbg_on = false;
   int force_bn = 0;
+  long long *stamps = nullptr;
+  int force_stages = 0;
+  uint32_t dbg_flags = 0;
 };
 
 TcState *state(b200_ctx *ctx) {
@@ -331,36 +465,39 @@ int get_map(b200_ctx *ctx, TcState *s, const float *ptr, uint64_t d0, uint64_t d
   return B200_OK;
 }
 
-int pick_bn(int M, int N, int sm_count) {
-  // N tile: multiple of 16 in [16, 256].  Prefer the widest tile that still yields >= ~0.85 wave
-  // of the machine; otherwise the tile that maximises SM coverage.
+int pick_bn(int M, int N, int K, int sm_count) {
+  // Measured on B200 (tools/gemm_stamps.py): one kind::tf32 M=128 instruction costs ~150 cycles for every
+  // N <= 256 (the A read from shared memory is the floor), so a 32-wide k-block costs >= ~610 cycles per
+  // CTA whatever the tile width; when many CTAs stream at once the L2->SM fabric (~7.3 KB/cycle for the
+  // whole chip) becomes the bound instead.  Pick the N tile (multiple of 32, or 16 for N <= 16) that
+  // minimises   waves * k-blocks * max(610, active*(16 KiB + 128 B * BN)/7300)  +  exposed epilogue.
   if (N <= 16) return 16;
   const int tiles_m = (M + BM - 1) / BM;
-  int best = 16;
-  double best_score = -1.0;
-  for (int bn = 256; bn >= 32; bn -= 16) {
+  const double num_k = (double)((K + BK - 1) / BK);
+  int best = 32;
+  double best_cost = 1e30;
+  for (int bn = 256; bn >= 32; bn -= 32) {
     const int tn = (N + bn - 1) / bn;
     const long tiles = (long)tiles_m * tn;
     const long waves = (tiles + sm_count - 1) / sm_count;
-    // useful work fraction: real columns / padded columns, times wave occupancy; wide tiles are
-    // cheaper per flop on shared-memory bandwidth (A is re-read per N tile)
-    const double col_eff = (double)N / ((double)tn * bn);
-    const double occ = (double)tiles / ((double)waves * sm_count);
-    const double width = bn >= 192 ? 1.0 : (bn >= 128 ? 0.92 : (bn >= 64 ? 0.75 : 0.5));
-    const double score = col_eff * occ * width;
-    if (score > best_score + 1e-9) { best_score = score; best = bn; }
+    const double active = (double)(tiles < sm_count ? tiles : sm_count);
+    const double kblock = fmax(610.0, active * (16384.0 + 128.0 * bn) / 7300.0);
+    const double cost = (double)waves * num_k * kblock + (bn / 32) * 500.0;
+    if (cost < best_cost - 1e-6) { best_cost = cost; best = bn; }
   }
   return best;
 }
 
 template <bool AK, bool BKM>
-int launch(b200_ctx *ctx, TcState *s, int idx, const CUtensorMap &ma, const CUtensorMap &mb, const TcParams &p, int grid) {
+int launch(b200_ctx *ctx, TcState *s, int idx, const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &mc,
+           const TcParams &p, int grid) {
   auto kern = gemm_tc_kernel<AK, BKM>;
   if (!s->attr_set[idx]) {
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
     s->attr_set[idx] = true;
   }
-  kern<<<grid, NTHREADS, SMEM_BYTES, ctx->stream>>>(ma, mb, p);
+  const size_t smem = (size_t)p.stages * p.stage_bytes + SMEM_EXTRA;
+  kern<<<grid, NTHREADS, smem, ctx->stream>>>(ma, mb, mc, p);
   LAUNCH_CHECK(ctx);
   return B200_OK;
 }
@@ -372,6 +509,17 @@ void gemm_tc_destroy(b200_ctx *ctx) {
     delete (TcState *)ctx->tc_state;
     ctx->tc_state = nullptr;
   }
+}
+
+// debug hook: per-CTA clock64 stamps (device buffer of 8*grid int64, or NULL to switch off)
+extern "C" int b200_debug_tc_stamps(b200_ctx *ctx, long long *stamps_dev) {
+  state(ctx)->stamps = stamps_dev;
+  return B200_OK;
+}
+extern "C" int b200_debug_tc_stages(b200_ctx *ctx, int stages) {
+  state(ctx)->force_stages = stages & 0xff;
+  state(ctx)->dbg_flags = (uint32_t)stages >> 8;
+  return B200_OK;
 }
 
 // debug hook: override descriptor fields {a_lbo,a_sbo,a_layout,a_kstep,b_lbo,b_sbo,b_layout,b_kstep}
@@ -396,10 +544,17 @@ int gemm_tc(b200_ctx *ctx, int transA, int transB, int M, int N, int K, const fl
 
   TcParams p;
   p.M = M; p.N = N; p.K = K;
-  p.BN = s->force_bn ? s->force_bn : pick_bn(M, N, ctx->sm_count);
+  p.BN = s->force_bn ? s->force_bn : pick_bn(M, N, K, ctx->sm_count);
+  // the ring is as deep as shared memory allows: loads are latency/bandwidth bound, so bytes in flight matter
+  p.stage_bytes = (uint32_t)A_BYTES + (b_k ? (uint32_t)p.BN * BK * 4 : (uint32_t)((p.BN + 31) / 32) * 4096u);
+  p.stages = (SMEM_MAX - SMEM_EXTRA) / (int)p.stage_bytes;
+  if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
+  if (s->force_stages > 0 && s->force_stages < p.stages) p.stages = s->force_stages;
   p.ldc = ldc;
   p.C = C;
   p.ep = ep;
+  p.stamps = s->stamps;
+  p.dbg_flags = s->dbg_flags;
   // K-major, SWIZZLE_128B: rows of 128 B, 8-row atoms 1 KiB apart (SBO), +32 B per UMMA_K step
   // MN-major fp32, 128B swizzle / 32 B atoms: 4-row k-groups 512 B apart (SBO), 32-wide MN chunks
   // one 4 KiB TMA box apart (LBO), two k-groups (1 KiB) per UMMA_K step
@@ -423,10 +578,20 @@ int gemm_tc(b200_ctx *ctx, int transA, int transB, int M, int N, int K, const fl
   else st = get_map(ctx, s, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, &mb);
   if (st) return st;
 
-  const int tiles = ((M + BM - 1) / BM) * ((N + p.BN - 1) / p.BN);
+  // C goes out through TMA stores of 32x32 boxes when its layout allows (16-byte aligned base and pitch);
+  // a box may only spill over the right edge of its N tile if that is also the edge of the matrix
+  CUtensorMap mc = ma;
+  const int tiles_n = (N + p.BN - 1) / p.BN;
+  p.tma_store = ((((uintptr_t)C) & 15) == 0 && (ldc & 3) == 0 && ((p.BN & 31) == 0 || tiles_n == 1) && !(s->dbg_flags & 8)) ? 1 : 0;
+  if (p.tma_store) {
+    st = get_map(ctx, s, C, (uint64_t)N, (uint64_t)M, (uint64_t)ldc, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B, &mc);
+    if (st) return st;
+  }
+
+  const int tiles = ((M + BM - 1) / BM) * tiles_n;
   const int grid = tiles < ctx->sm_count ? tiles : ctx->sm_count;
-  if (a_k && b_k) return launch<true, true>(ctx, s, 0, ma, mb, p, grid);
-  if (a_k && !b_k) return launch<true, false>(ctx, s, 1, ma, mb, p, grid);
-  if (!a_k && b_k) return launch<false, true>(ctx, s, 2, ma, mb, p, grid);
-  return launch<false, false>(ctx, s, 3, ma, mb, p, grid);
+  if (a_k && b_k) return launch<true, true>(ctx, s, 0, ma, mb, mc, p, grid);
+  if (a_k && !b_k) return launch<true, false>(ctx, s, 1, ma, mb, mc, p, grid);
+  if (!a_k && b_k) return launch<false, true>(ctx, s, 2, ma, mb, mc, p, grid);
+  return launch<false, false>(ctx, s, 3, ma, mb, mc, p, grid);
 }
