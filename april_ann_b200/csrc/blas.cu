@@ -58,6 +58,8 @@ extern "C" int b200_linear_fwd(b200_ctx *ctx, int M, int N, int K, const float *
   ARG_CHECK(act == B200_ACT_NONE || act == B200_ACT_LOGISTIC || act == B200_ACT_TANH ||
                 act == B200_ACT_RELU || act == B200_ACT_LINEAR,
             "only element-wise activations fuse into the contraction");
+  if (skinny_applicable(M, N, K))
+    return skinny_fwd(ctx, M, N, K, X, ldx, W, ldw, bias, (act == B200_ACT_LINEAR) ? B200_ACT_NONE : act, Y, ldy);
   GemmEpilogue ep;
   ep.bias = bias;
   ep.act = (act == B200_ACT_LINEAR) ? B200_ACT_NONE : act;
@@ -69,9 +71,12 @@ extern "C" int b200_linear_bwd_data(b200_ctx *ctx, int M, int N, int K, const fl
                                     const float *W, int ldw, int act_prev, const float *Yprev,
                                     int ldyp, float *dX, int lddx) {
   ARG_CHECK(ctx && dY && W && dX, "NULL pointer");
+  const bool has_prev = (act_prev == B200_ACT_LOGISTIC || act_prev == B200_ACT_TANH || act_prev == B200_ACT_RELU);
+  if (has_prev) ARG_CHECK(Yprev, "Yprev is required when act_prev is set");
+  if (skinny_applicable(M, N, K))
+    return skinny_bwd_data(ctx, M, N, K, dY, lddy, W, ldw, has_prev ? act_prev : B200_ACT_NONE, Yprev, ldyp, dX, lddx);
   GemmEpilogue ep;
-  if (act_prev == B200_ACT_LOGISTIC || act_prev == B200_ACT_TANH || act_prev == B200_ACT_RELU) {
-    ARG_CHECK(Yprev, "Yprev is required when act_prev is set");
+  if (has_prev) {
     ep.dact = act_prev;
     ep.dsrc = Yprev;
     ep.ld_dsrc = ldyp;
@@ -84,6 +89,7 @@ extern "C" int b200_linear_bwd_weight(b200_ctx *ctx, int M, int N, int K, const 
                                       const float *X, int ldx, float scale, float beta, float *dW,
                                       int lddw, float *db) {
   ARG_CHECK(ctx && dY && X && dW, "NULL pointer");
+  if (skinny_applicable(M, N, K)) return skinny_bwd_weight(ctx, M, N, K, dY, lddy, X, ldx, scale, beta, dW, lddw, db);
   GemmEpilogue ep;
   ep.alpha = scale;
   ep.beta = beta;

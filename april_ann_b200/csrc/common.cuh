@@ -129,6 +129,15 @@ int gemm_tc(b200_ctx *ctx, int transA, int transB, int M, int N, int K, const fl
 int gemm_dispatch(b200_ctx *ctx, int transA, int transB, int M, int N, int K, const float *A,
                   int lda, const float *B, int ldb, float *C, int ldc, const GemmEpilogue &ep);
 void gemm_tc_destroy(b200_ctx *ctx);
+// skinny.cu: layers with N <= 16 output neurons and the bias gradient (HBM-bound, exact fp32)
+bool skinny_applicable(int M, int N, int K);
+int skinny_fwd(b200_ctx *ctx, int M, int N, int K, const float *X, int ldx, const float *W, int ldw, const float *bias,
+               int act, float *Y, int ldy);
+int skinny_bwd_data(b200_ctx *ctx, int M, int N, int K, const float *dY, int lddy, const float *W, int ldw, int dact,
+                    const float *Yprev, int ldyp, float *dX, int lddx);
+int skinny_bwd_weight(b200_ctx *ctx, int M, int N, int K, const float *dY, int lddy, const float *X, int ldx, float scale,
+                      float beta, float *dW, int lddw, float *db);
+int colsum_scaled(b200_ctx *ctx, int M, int N, const float *dy, int ld, float scale, float beta, float *out);
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

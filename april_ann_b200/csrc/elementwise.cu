@@ -92,27 +92,6 @@ __global__ void __launch_bounds__(TPB) bias_fwd_kernel(int M, int N, const float
     y[i] = x[i] + __ldg(b + (i % N));
 }
 
-// db[n] = beta*db[n] + scale * sum_m dy[m,n]   (bias_component.cc:87-122; the reference's
-// axpyLoopKernel serialises threads for this, axpy.cu:127-136).  One CTA per 32 columns:
-// 8 warps stride over the rows with coalesced 128-byte reads, then a smem tree.
-__global__ void __launch_bounds__(256) bias_grad_kernel(int M, int N, const float *__restrict__ dy, int ld,
-                                                        float scale, float beta, float *__restrict__ db) {
-  __shared__ float part[8][33];
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int n = blockIdx.x * 32 + lane;
-  float s = 0.0f;
-  if (n < N)
-    for (int m = w; m < M; m += 8) s += __ldg(dy + (size_t)m * ld + n);
-  part[w][lane] = s;
-  __syncthreads();
-  if (w == 0 && n < N) {
-    float t = 0.0f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) t += part[i][lane];
-    db[n] = (beta != 0.0f ? beta * db[n] : 0.0f) + scale * t;
-  }
-}
-
 // ---- reductions ----------------------------------------------------------------
 template <bool SQ, bool ACCUM>
 __global__ void __launch_bounds__(TPB) reduce_partial_kernel(size_t n, const float *__restrict__ x, float *__restrict__ part) {
@@ -246,9 +225,8 @@ extern "C" int b200_bias_grad(b200_ctx *ctx, int M, int N, const float *dy, int 
                               float beta, float *db) {
   ARG_CHECK(ctx && dy && db, "NULL pointer");
   if (N <= 0) return B200_OK;
-  bias_grad_kernel<<<(N + 31) / 32, 256, 0, ctx->stream>>>(M, N, dy, lddy, scale, beta, db);
-  LAUNCH_CHECK(ctx);
-  return B200_OK;
+  // db[n] = beta*db[n] + scale * sum_m dy[m,n]  (bias_component.cc:87-122): two-stage column sum, skinny.cu
+  return colsum_scaled(ctx, M, N, dy, lddy, scale, beta, db);
 }
 extern "C" int b200_loss_accumulate(b200_ctx *ctx, int M, const float *loss_rows, double *stats) {
   ARG_CHECK(ctx && loss_rows && stats, "NULL pointer");

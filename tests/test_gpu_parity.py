@@ -104,6 +104,46 @@ def test_linear_bwd_weight_scale_beta_and_bias(ops):
     assert rel_l2(db2, db0 + scale * dY.sum(axis=0)) < F32_TOL
 
 
+@pytest.mark.parametrize("M,N,K", [(1024, 10, 2048), (37, 3, 50), (130, 16, 132), (1, 10, 64), (4096, 10, 512)])
+@pytest.mark.parametrize("act", [None, "tanh", "relu"])
+def test_skinny_output_layer_passes(ops, M, N, K, act):
+    """Layers with <= 16 output neurons (the 10-class output layer of every BASELINE MLP) take the
+    HBM-bound exact-fp32 kernels of skinny.cu: forward, data gradient with the previous layer's
+    derivative, weight gradient with scale/beta and the fused bias gradient."""
+    X, W, b = rnd_mat(90, M, K), rnd_mat(91, N, K, lo=-0.2, hi=0.2), rnd_mat(92, N)
+    f = {None: lambda z: z, "tanh": A.antisym_logistic, "relu": A.relu}[act]
+    want = f((X.astype(np.float64) @ W.T.astype(np.float64) + b).astype(np.float32))
+    assert rel_l2(ops.linear_fwd(X, W, b, act), want) < F32_TOL
+    dY = rnd_mat(93, M, N)
+    yprev = f(rnd_mat(94, M, K, lo=-2, hi=2)) if act else None
+    dx = (dY.astype(np.float64) @ W.astype(np.float64)).astype(np.float32)
+    if act == "tanh":
+        dx = A.antisym_logistic_der(yprev) * dx
+    elif act == "relu":
+        dx = A.relu_der(yprev) * dx
+    assert rel_l2(ops.linear_bwd_data(dY, W, act, yprev), dx) < F32_TOL
+    scale = float(1.0 / np.sqrt(M))
+    dW0, db0 = rnd_mat(95, N, K), rnd_mat(96, N)
+    dW, db = ops.linear_bwd_weight(dY, X, scale=scale, beta=1.0, dW0=dW0, db0=db0)
+    assert rel_l2(dW, dW0 + scale * (dY.T.astype(np.float64) @ X.astype(np.float64))) < F32_TOL
+    assert rel_l2(db, db0 + scale * dY.astype(np.float64).sum(axis=0)) < F32_TOL
+    dW, db = ops.linear_bwd_weight(dY, X, scale=scale)
+    assert rel_l2(dW, scale * (dY.T.astype(np.float64) @ X.astype(np.float64))) < F32_TOL
+    assert rel_l2(db, scale * dY.astype(np.float64).sum(axis=0)) < F32_TOL
+
+
+@pytest.mark.parametrize("M,N", [(1024, 2048), (1000, 33), (5, 4), (8192, 4096), (77, 130)])
+def test_bias_gradient_column_sums(ops, M, N):
+    """bias_component.cc:87-122 as a two-stage deterministic column sum."""
+    dY = rnd_mat(97, M, N)
+    X = rnd_mat(98, M, 8)
+    _, db = ops.linear_bwd_weight(dY, X, scale=0.25)
+    assert rel_l2(db, 0.25 * dY.astype(np.float64).sum(axis=0)) < F32_TOL
+    db0 = rnd_mat(99, N)
+    _, db = ops.linear_bwd_weight(dY, X, scale=0.25, beta=1.0, dW0=np.zeros((N, 8), np.float32), db0=db0)
+    assert rel_l2(db, db0 + 0.25 * dY.astype(np.float64).sum(axis=0)) < F32_TOL
+
+
 # ------------------------------------------------------------------ activations / row kernels
 @pytest.mark.parametrize("act", ["logistic", "tanh", "relu"])
 def test_actf_elementwise(ops, act):
