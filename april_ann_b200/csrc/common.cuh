@@ -21,6 +21,7 @@ struct b200_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t comm_stream = nullptr;
   cudaEvent_t ev_compute = nullptr, ev_comm = nullptr;
+  cudaEvent_t ev_bucket[16] = {};        // completion of the async gradient buckets
   uint64_t launches = 0;
   // caching pool: size -> free blocks ; ptr -> size for live blocks
   std::multimap<size_t, void *> free_blocks;

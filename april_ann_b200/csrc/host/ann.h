@@ -10,6 +10,7 @@
 #pragma once
 #include <stdint.h>
 
+#include <functional>
 #include <map>
 #include <memory>
 #include <stdexcept>
@@ -242,6 +243,13 @@ class StackANNComponent : public ANNComponent {
   // set by the trainer: stop before a trailing row-wise activation so that the loss kernel
   // can fuse log_softmax + loss + gradient
   bool defer_last_actf = false;
+  // trainer: compute every component's weight gradients inside doBackprop, as soon as its error
+  // input exists (reverse layer order), so that finished gradients can be all-reduced while the
+  // rest of the backward pass runs.  on_gradients_ready(component) fires after each one.
+  MatrixDict *interleave_grads = nullptr;
+  std::function<void(ANNComponent *)> on_gradients_ready;
+  void prepareGradScales();   // sets grad_scale of every weight-bearing component from grad_bunch
+  const std::vector<ANNComponent *> &flatComponents() const { return flat; }
  private:
   void flatten(std::vector<ANNComponent *> &out);
   std::vector<ANNComponent *> flat;
@@ -316,6 +324,7 @@ class SupervisedTrainer {
   void stage(const float *x, const float *t, int bunch);   // async H2D into the staging buffers
   void stepStaged(int bunch);                              // train step on the staged bunch
   std::vector<std::string> weightNames() const { return weights_order; }
+  size_t dp_bucket_bytes = 4u << 20;   // gradients are all-reduced in buckets of at least this size
   MatrixPtr weight(const std::string &n) { return weights_table.at(n); }
   MatrixPtr gradient(const std::string &n) { return grads.at(n); }
   double norm2(const std::string &pattern);
@@ -333,7 +342,8 @@ class SupervisedTrainer {
   bool keep_gradients = false;    // write the regularised gradient back (observable grads; +4 B/param)
   bool use_cuda_graph = true;
   MatrixDict weights_table, grads, updates;
-  std::vector<std::string> weights_order;
+  std::vector<std::string> weights_order;   // sorted names (initialisation / API order)
+  std::vector<std::string> arena_order;     // layout of the flat arenas: reverse layer order
   MatrixPtr weights_arena, grads_arena, updates_arena;
   MatrixPtr last_loss_rows, last_output;
   int dp_nranks = 1, dp_rank = 0;

@@ -475,6 +475,12 @@ MatrixPtr StackANNComponent::doBackprop(const MatrixPtr &err) {
   const int n = (int)flat.size();
   while (i >= 0) {
     ANNComponent *c = flat[i];
+    if (interleave_grads && c->hasWeightsName() && cur) {
+      // the error input of this component is final: its weight gradients can be computed now
+      c->error_input = cur;
+      c->computeAllGradients(*interleave_grads);
+      if (on_gradients_ready) on_gradients_ready(c);
+    }
     if (fuse) {
       auto *la = dynamic_cast<ActivationFunctionANNComponent *>(c);
       if (la && i == n - 1 && last_actf_backprop_is_identity) {
@@ -528,7 +534,7 @@ MatrixPtr StackANNComponent::doBackprop(const MatrixPtr &err) {
   return cur;
 }
 
-void StackANNComponent::computeAllGradients(MatrixDict &grads) {
+void StackANNComponent::prepareGradScales() {
   // total uses of every weights matrix in this step -> 1/sqrt(shared_count * bunch)
   std::map<std::string, int> uses;
   for (auto *c : flat)
@@ -538,8 +544,12 @@ void StackANNComponent::computeAllGradients(MatrixDict &grads) {
     int nuse = uses[c->getWeightsName()];
     if (nuse <= 0) nuse = 1;
     c->grad_scale = (grad_bunch > 0.0f) ? (float)(1.0 / sqrt((double)nuse * (double)grad_bunch)) : 1.0f;
-    c->computeAllGradients(grads);
   }
+}
+void StackANNComponent::computeAllGradients(MatrixDict &grads) {
+  prepareGradScales();
+  for (auto *c : flat)
+    if (c->hasWeightsName()) c->computeAllGradients(grads);
 }
 
 ComponentPtr makeHyperplane(const std::string &name, unsigned in, unsigned out, const std::string &dot_name,

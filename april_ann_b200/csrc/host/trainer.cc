@@ -6,6 +6,7 @@
 // statistics, step counter) is enqueued on one stream and, once warm, replayed as a CUDA graph.
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -140,6 +141,7 @@ SupervisedTrainer::SupervisedTrainer(b200_ctx *ctx, const std::shared_ptr<StackA
                                      int bunch_size)
     : ctx(ctx), net(net), loss(ctx, loss_kind, 0), bunch_size(bunch_size) {
   if (!ctx) throw Error(B200_ERR_CUDA, "trainer needs a device context: this build has no CPU path");
+  if (const char *e = getenv("B200_DP_BUCKET_MB")) dp_bucket_bytes = (size_t)(atof(e) * 1048576.0);
   void *p;
   check(b200_malloc(ctx, &p, 2 * sizeof(int64_t)));
   count_dev = (int64_t *)p;
@@ -161,12 +163,25 @@ void SupervisedTrainer::build(unsigned input, unsigned output) {
   weights_order.clear();
   for (auto &kv : discovered) weights_order.push_back(kv.first);
   std::sort(weights_order.begin(), weights_order.end());  // supervised.lua:680-681
-  // pass 2: re-home every tensor in flat arenas (weights / gradients / momentum), sorted-name
-  // order, 512-byte aligned -- one all-reduce and one SGD launch cover all of them
-  std::vector<size_t> offs;
+  // pass 2: re-home every tensor in flat arenas (weights / gradients / momentum), 512-byte aligned,
+  // laid out in REVERSE layer order = the order in which the backward pass finishes gradients, so
+  // that a bucket of finished gradients is one contiguous range for the all-reduce
+  arena_order.clear();
+  {
+    const auto &flat = net->flatComponents();
+    for (auto it = flat.rbegin(); it != flat.rend(); ++it) {
+      if (!(*it)->hasWeightsName()) continue;
+      const std::string &wn = (*it)->getWeightsName();
+      if (discovered.count(wn) && std::find(arena_order.begin(), arena_order.end(), wn) == arena_order.end())
+        arena_order.push_back(wn);
+    }
+    for (auto &n : weights_order)
+      if (std::find(arena_order.begin(), arena_order.end(), n) == arena_order.end()) arena_order.push_back(n);
+  }
+  std::map<std::string, size_t> offs;
   size_t total = 0;
-  for (auto &n : weights_order) {
-    offs.push_back(total);
+  for (auto &n : arena_order) {
+    offs[n] = total;
     total += (discovered[n]->size() + 127) & ~size_t(127);
   }
   total_params = 0;
@@ -182,9 +197,9 @@ void SupervisedTrainer::build(unsigned input, unsigned output) {
   for (size_t i = 0; i < weights_order.size(); ++i) {
     const std::string &n = weights_order[i];
     const std::vector<int> &d = discovered[n]->dims;
-    weights_table[n] = Matrix::view(weights_arena, offs[i], d);
-    grads[n] = Matrix::view(grads_arena, offs[i], d);
-    updates[n] = Matrix::view(updates_arena, offs[i], d);
+    weights_table[n] = Matrix::view(weights_arena, offs[n], d);
+    grads[n] = Matrix::view(grads_arena, offs[n], d);
+    updates[n] = Matrix::view(updates_arena, offs[n], d);
     total_params += discovered[n]->size();
   }
   ComponentDict comps2;
@@ -237,10 +252,10 @@ void SupervisedTrainer::randomizeWeights(MTRand &rnd, double inf, double sup, bo
 }
 
 void SupervisedTrainer::uploadSgdTable() {
-  const int nt = (int)weights_order.size();
+  const int nt = (int)arena_order.size();
   sgd_host.resize(nt);
   for (int i = 0; i < nt; ++i) {
-    const std::string &n = weights_order[i];
+    const std::string &n = arena_order[i];
     b200_sgd_tensor &t = sgd_host[i];
     memset(&t, 0, sizeof(t));
     t.w = weights_table[n]->data;
@@ -299,13 +314,69 @@ void SupervisedTrainer::runStep(const MatrixPtr &x, const MatrixPtr &t, int glob
     grad = loss.computeGradient(out, t);
     net->last_actf_backprop_is_identity = false;
   }
-  net->doBackprop(grad);
-  net->last_actf_backprop_is_identity = false;
+  // backward pass with the weight gradients interleaved (reverse layer order).  With a replica
+  // group, finished gradients are all-reduced bucket by bucket on the communication stream while
+  // the rest of the backward pass runs, and each bucket is updated as soon as it has arrived.
   net->grad_bunch = smooth_gradients ? (float)global_bunch : 0.0f;
-  net->computeAllGradients(grads);
-  if (dp_nranks > 1) check(b200_allreduce_sum(ctx, grads_arena->data, grads_arena->size()));
-  check(b200_sgd_multi_tensor(ctx, (int)sgd_host.size(), sgd_dev, sgd_host.data(), optimizer.getOption("decay"),
-                              count_dev, keep_gradients ? 1 : 0));
+  net->prepareGradScales();
+  const int nt = (int)arena_order.size();
+  std::vector<char> done(nt, 0);
+  std::vector<std::pair<int, int>> buckets;   // [first, last) tensor indices in arena order
+  int next = 0;
+  auto flush = [&](bool force) {
+    int hi = next;
+    size_t bytes = 0;
+    while (hi < nt && done[hi]) { bytes += grads[arena_order[hi]]->size() * sizeof(float); ++hi; }
+    if (hi == next) return;
+    if (!force && bytes < dp_bucket_bytes && hi < nt) return;
+    if ((int)buckets.size() >= 15 && hi < nt) return;   // keep one slot for the tail
+    float *base = grads[arena_order[next]]->data;
+    const MatrixPtr &last = grads[arena_order[hi - 1]];
+    const size_t count = (size_t)(last->data - base) + last->size();
+    check(b200_allreduce_sum_async(ctx, base, count, (int)buckets.size()));
+    buckets.emplace_back(next, hi);
+    next = hi;
+  };
+  if (dp_nranks > 1) {
+    net->on_gradients_ready = [&](ANNComponent *c) {
+      // a tensor is final once every component that shares it has contributed
+      const std::string &wn = c->getWeightsName();
+      bool pending = false, seen = false;
+      const auto &flat = net->flatComponents();
+      for (auto *o : flat) {
+        if (o == c) { seen = true; continue; }
+        if (!seen && o->hasWeightsName() && o->getWeightsName() == wn) pending = true;   // earlier layers come later
+      }
+      if (pending) return;
+      for (int i = 0; i < nt; ++i)
+        if (arena_order[i] == wn) done[i] = 1;
+      flush(false);
+    };
+  }
+  net->interleave_grads = &grads;
+  try {
+    net->doBackprop(grad);
+  } catch (...) {
+    net->interleave_grads = nullptr;
+    net->on_gradients_ready = nullptr;
+    throw;
+  }
+  net->interleave_grads = nullptr;
+  net->on_gradients_ready = nullptr;
+  net->last_actf_backprop_is_identity = false;
+  if (dp_nranks > 1) {
+    for (int i = 0; i < nt; ++i) done[i] = 1;   // tensors no component touched this step stay zero: reduce them too
+    flush(true);
+    for (size_t b = 0; b < buckets.size(); ++b) {
+      check(b200_comm_wait(ctx, (int)b));
+      check(b200_sgd_multi_tensor(ctx, buckets[b].second - buckets[b].first, sgd_dev + buckets[b].first,
+                                  sgd_host.data() + buckets[b].first, optimizer.getOption("decay"), count_dev,
+                                  keep_gradients ? 1 : 0));
+    }
+  } else {
+    check(b200_sgd_multi_tensor(ctx, (int)sgd_host.size(), sgd_dev, sgd_host.data(), optimizer.getOption("decay"),
+                                count_dev, keep_gradients ? 1 : 0));
+  }
   check(b200_counter_increment(ctx, count_dev));
   loss.accumLoss(rows);
   last_loss_rows = rows;

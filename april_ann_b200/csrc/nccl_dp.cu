@@ -129,6 +129,29 @@ static int allreduce_impl(b200_ctx *ctx, void *buf, size_t n, int dtype) {
   ctx->launches++;
   return B200_OK;
 }
+extern "C" int b200_allreduce_sum_async(b200_ctx *ctx, float *buf, size_t n, int slot) {
+  ARG_CHECK(ctx && buf, "NULL pointer");
+  ARG_CHECK(slot >= 0 && slot < 16, "slot out of range");
+  if (ctx->nranks <= 1 || n == 0) return B200_OK;
+  ARG_CHECK(ctx->nccl_comm, "communicator not initialised (b200_comm_init)");
+  NcclApi *a = nccl();
+  if (!a) return B200_ERR_NCCL;
+  int st = fence_in(ctx);   // the bucket's gradients are complete on the compute stream
+  if (st) return st;
+  st = nccl_check(a->AllReduce(buf, buf, n, ncclFloat32, ncclSum, (ncclComm_t)ctx->nccl_comm, ctx->comm_stream),
+                  "ncclAllReduce");
+  if (st) return st;
+  ctx->launches++;
+  CUDA_TRY(cudaEventRecord(ctx->ev_bucket[slot], ctx->comm_stream));
+  return B200_OK;
+}
+extern "C" int b200_comm_wait(b200_ctx *ctx, int slot) {
+  ARG_CHECK(ctx, "NULL pointer");
+  ARG_CHECK(slot >= 0 && slot < 16, "slot out of range");
+  if (ctx->nranks <= 1) return B200_OK;
+  CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_bucket[slot], 0));
+  return B200_OK;
+}
 extern "C" int b200_allreduce_sum(b200_ctx *ctx, float *buf, size_t n) { return allreduce_impl(ctx, buf, n, ncclFloat32); }
 extern "C" int b200_allreduce_sum_f64(b200_ctx *ctx, double *buf, size_t n) {
   return allreduce_impl(ctx, buf, n, ncclFloat64);

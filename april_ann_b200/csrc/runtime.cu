@@ -58,6 +58,7 @@ extern "C" int b200_create(int device, b200_ctx **out) {
   CUDA_TRY(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
   CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_compute, cudaEventDisableTiming));
   CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_comm, cudaEventDisableTiming));
+  for (auto &e : ctx->ev_bucket) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   *out = ctx;
   return B200_OK;
 }
@@ -85,6 +86,7 @@ extern "C" int b200_destroy(b200_ctx *ctx) {
   if (ctx->scratch) cudaFree(ctx->scratch);
   cudaEventDestroy(ctx->ev_compute);
   cudaEventDestroy(ctx->ev_comm);
+  for (auto &e : ctx->ev_bucket) if (e) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->stream);
   cudaStreamDestroy(ctx->comm_stream);
   delete ctx;

@@ -210,6 +210,11 @@ int b200_comm_destroy(b200_ctx *ctx);
 int b200_allreduce_sum(b200_ctx *ctx, float *buf, size_t n);      /* in place, on the comm stream,
                                                                      ordered after/before the compute stream */
 int b200_allreduce_sum_f64(b200_ctx *ctx, double *buf, size_t n);
+/* bucketed overlap: the all-reduce runs on the communication stream after everything enqueued so far
+ * on the compute stream; b200_comm_wait(slot) makes the compute stream wait for that bucket
+ * (slot in [0, 16)).  Both are capturable in a CUDA graph. */
+int b200_allreduce_sum_async(b200_ctx *ctx, float *buf, size_t n, int slot);
+int b200_comm_wait(b200_ctx *ctx, int slot);
 int b200_broadcast(b200_ctx *ctx, float *buf, size_t n, int root);
 
 #ifdef __cplusplus

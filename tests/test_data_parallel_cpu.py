@@ -1,0 +1,101 @@
+"""Host-side data-parallel logic on CPU: world_size-2 gloo group (no GPU).  Each rank runs the
+oracle's forward/backward on its rows of a global bunch, raw gradient sums are all-reduced, and
+the reference's smoothing factor is applied with the GLOBAL bunch size
+(april_ann_b200/parallel.py) -- the result must equal one single-process step on the whole bunch,
+which is the property the NCCL path relies on."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+TOPO = "12 inputs 9 tanh 7 relu 4 log_softmax"
+GLOBAL_BUNCH = 10
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _make_trainer():
+    from oracle import MTRand
+    from oracle import april as A
+    tr = A.SupervisedTrainer(A.mlp_all_all(TOPO), A.MultiClassCrossEntropy(), GLOBAL_BUNCH).build()
+    tr.set_option("learning_rate", 0.1)
+    tr.set_option("momentum", 0.5)
+    tr.set_option("weight_decay", 1e-3)
+    tr.set_layerwise_option("b.", "weight_decay", 0)
+    tr.randomize_weights(random=MTRand(1234), inf=-1, sup=1, use_fanin=True, use_fanout=True)
+    return tr
+
+
+def _data():
+    from oracle import MTRand
+    r = MTRand(99)
+    x = (r.rand_array(GLOBAL_BUNCH * 12, 2.0) - 1.0).astype(np.float32).reshape(GLOBAL_BUNCH, 12)
+    t = np.zeros((GLOBAL_BUNCH, 4), dtype=np.float32)
+    t[np.arange(GLOBAL_BUNCH), [r.randInt(0, 3) for _ in range(GLOBAL_BUNCH)]] = 1.0
+    return x, t
+
+
+def _worker(rank, world, port, out_dir):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group(backend="gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    # the package needs the built library to import; only its host-side helpers are used here
+    from april_ann_b200.parallel import shard_rows, dp_grad_scale
+    tr = _make_trainer()
+    x, t = _data()
+    lo, hi = shard_rows(GLOBAL_BUNCH, rank, world)
+    for _ in range(3):
+        out = tr.net.forward(x[lo:hi], True)
+        _, rows = tr.loss.compute_loss(out, t[lo:hi])
+        tr.net.backprop(tr.loss.gradient(out, t[lo:hi]))
+        grads, counts = {}, {}
+        tr.net.compute_gradients(grads, counts)
+        for name in sorted(grads):
+            g = torch.from_numpy(grads[name])
+            dist.all_reduce(g, op=dist.ReduceOp.SUM)          # raw sums over rows -> global sum
+            grads[name] *= np.float32(dp_grad_scale(counts.get(name, 0) or 1, GLOBAL_BUNCH))
+        tr.optimizer.execute(tr.weights, grads)
+    np.savez(os.path.join(out_dir, "rank%d.npz" % rank), **tr.weights)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_shard_rows_partitions_every_bunch():
+    from april_ann_b200.parallel import shard_rows
+    for n in (1, 7, 8, 1024, 1025):
+        for world in (1, 2, 3, 8):
+            spans = [shard_rows(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_two_rank_gloo_step_equals_single_process_step(tmp_path):
+    import torch.multiprocessing as mp
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    ref = _make_trainer()
+    x, t = _data()
+    for _ in range(3):
+        ref.train_step(x, t)
+    w0 = np.load(os.path.join(str(tmp_path), "rank0.npz"))
+    w1 = np.load(os.path.join(str(tmp_path), "rank1.npz"))
+    for name in ref.weights:
+        assert np.array_equal(w0[name], w1[name]), name            # replicas stay identical
+        err = np.abs(w0[name] - ref.weights[name]).max()
+        assert err < 2e-6, (name, err)                              # == one step on the global bunch
