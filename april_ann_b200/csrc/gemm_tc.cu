@@ -29,7 +29,7 @@ constexpr int MAX_STAGES = 8;
 constexpr int MAX_BN = 256;
 constexpr int A_BYTES = BM * BK * 4;          // 16 KiB
 constexpr int STAGING_BYTES = 4 * 2 * 32 * 32 * 4;   // two 32x32 fp32 staging buffers per epilogue warp
-constexpr int SMEM_EXTRA = STAGING_BYTES + 256 /*barriers*/ + 1024 /*align slack*/;
+constexpr int SMEM_EXTRA = STAGING_BYTES + 256 /*barriers*/ + 512 /*per-warp bias slots*/ + 1024 /*align slack*/;
 constexpr int SMEM_MAX = 227 * 1024;
 constexpr int NTHREADS = 192;
 constexpr int TMEM_COLS = 512;   // two 256-column accumulator stages
@@ -108,6 +108,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// thread-block cluster helpers (split-K pairs)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
 // SBO>>4 [32,46), version=1 [46,48), layout type [61,64)
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
@@ -127,54 +141,101 @@ struct TcParams {
   uint32_t a_lbo, a_sbo, a_layout, a_kstep;
   uint32_t b_lbo, b_sbo, b_layout, b_kstep;
   uint32_t idesc;
+  int splitk;          // 1, or 2: a cluster of two CTAs shares one output tile, each contracting half of K;
+                       //          the partial accumulators meet through distributed shared memory
   int tma_store;       // 1: the epilogue writes C through map_c (cp.async.bulk.tensor store), 0: direct stores
-  uint32_t dbg_flags;  // bring-up only: 8 = force direct stores instead of TMA stores
-  long long *stamps;   // bring-up only: per-CTA clock64 stamps [grid][8] (nullptr in production)
+  uint32_t dbg_flags;  // bring-up only: 8 = force direct stores instead of TMA stores, 16 = no split-K
+  long long *stamps;   // bring-up only: per-CTA clock64 stamps [grid][16] (nullptr in production)
 };
 
 // v = alpha*acc (+ bias) ; v = ACT(v) ; v *= DACT'(dsrc) ; v += beta*cold  -- ACT / DACT fixed at compile time
 template <int ACT, int DACT>
-__device__ __forceinline__ float epi_value(const GemmEpilogue &e, bool has_bias, bool has_c, float acc, float bias,
+__device__ __forceinline__ float epi_value(float alpha, float beta, bool has_bias, bool has_c, float acc, float bias,
                                            float dsrc, float cold) {
-  float v = e.alpha * acc;
+  float v = alpha * acc;
   if (has_bias) v += bias;
   if (ACT != B200_ACT_NONE) v = act_apply(ACT, v);
   if (DACT != B200_ACT_NONE) v *= act_deriv_from_output(DACT, dsrc);
-  if (has_c) v = fmaf(e.beta, cold, v);
+  if (has_c) v = fmaf(beta, cold, v);
   return v;
 }
 
 // Epilogue of one 128 x BN accumulator for one warp (32 TMEM lanes = 32 rows starting at m_base):
 // tcgen05.ld 32 columns at a time -> shared memory (transpose) -> global through a TMA store, or
 // direct row-contiguous stores when C cannot be described by a tensor map.
+// Every field of the parameter block is copied into a register up front: left in the struct they
+// were re-read from local memory for every element (ptxas kept a stack copy of the kernel parameters).
 template <int ACT, int DACT>
-__device__ __noinline__ void epilogue_tile(const TcParams &p, const CUtensorMap *map_c, uint32_t taddr, uint32_t stg,
-                                           int m_base, int n0, int lane, int &chunk) {
+__device__ __forceinline__ void epilogue_tile(const TcParams &p, const CUtensorMap *map_c, uint32_t taddr, uint32_t stg,
+                                              int m_base, int n0, int lane, int &chunk, int c_begin, int c_end,
+                                              uint32_t recv, uint32_t bias_slot) {
+  const float alpha = p.ep.alpha, beta = p.ep.beta;
+  const float *__restrict__ bias = p.ep.bias;
+  const float *__restrict__ dsrc = p.ep.dsrc;
+  const int ld_dsrc = p.ep.ld_dsrc, ldc = p.ldc, M = p.M;
+  float *__restrict__ C = p.C;
+  const bool tma_store = p.tma_store != 0;
   const int n_end = min(p.N, n0 + p.BN);
   const int cg = lane & 7;                       // 16-byte column group this lane handles after the transpose
-  const bool has_bias = p.ep.bias != nullptr, has_c = p.ep.beta != 0.0f;
+  const bool has_bias = bias != nullptr, has_c = beta != 0.0f;
   constexpr bool has_d = DACT != B200_ACT_NONE;
-  const bool c_vec = ((p.ldc & 3) == 0) && ((((uintptr_t)p.C) & 15) == 0);
-  const bool d_vec = !has_d || (((p.ep.ld_dsrc & 3) == 0) && ((((uintptr_t)p.ep.dsrc) & 15) == 0));
+  const bool c_vec = ((ldc & 3) == 0) && ((((uintptr_t)C) & 15) == 0);
+  const bool d_vec = !has_d || (((ld_dsrc & 3) == 0) && ((((uintptr_t)dsrc) & 15) == 0));
   // simple epilogues (alpha, bias, activation) are applied in the accumulator layout (lane = row);
   // the ones that read global memory per element (derivative source, old C) run after the transpose
-  const bool simple = p.tma_store && !has_d && !has_c;
-  for (int c0 = 0; c0 < p.BN; c0 += 32, ++chunk) {
+  const bool simple = tma_store && !has_d && !has_c;
+  // bring-up: phase durations of warp 2 lane 0, accumulated in registers, flushed once at the end
+  const bool timing = p.stamps != nullptr && threadIdx.x == 64;
+  long long tacc[6] = {0, 0, 0, 0, 0, 0};
+  long long tq = timing ? clock64() : 0;
+#define EPI_STAMP(i) do { if (timing) { const long long tn = clock64(); tacc[i] += tn - tq; tq = tn; } } while (0)
+  for (int c0 = c_begin; c0 < c_end; c0 += 32, ++chunk) {
     const uint32_t buf = stg + (uint32_t)(chunk & 1) * 4096u;
-    if (p.tma_store) {
+    if (tma_store) {
       // the bulk store that last read this buffer (two chunks ago) must have finished reading it
       if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
       __syncwarp();
     }
+    EPI_STAMP(0);
     uint32_t r[32];
     tmem_ld32(taddr + c0, r);                    // lane = accumulator row, 32 consecutive columns
+    EPI_STAMP(1);
     if (n0 + c0 >= n_end) break;
-    if (simple) {
+    if (recv) {
+      // split-K: add the peer CTA's partial sums of this chunk (same row-per-lane, XOR-swizzled layout)
+      const uint32_t rb = recv + (uint32_t)((c0 - c_begin) >> 5) * 4096u + (uint32_t)lane * 128u;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int n = n0 + c0 + j;
-        const float b = (has_bias && n < n_end) ? __ldg(p.ep.bias + n) : 0.0f;
-        r[j] = __float_as_uint(epi_value<ACT, DACT>(p.ep, has_bias, false, __uint_as_float(r[j]), b, 1.0f, 0.0f));
+      for (int g = 0; g < 8; ++g) {
+        float v[4];
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3])
+                     : "r"(rb + (uint32_t)((g ^ (lane & 7)) << 4)));
+#pragma unroll
+        for (int e = 0; e < 4; ++e) r[4 * g + e] = __float_as_uint(__uint_as_float(r[4 * g + e]) + v[e]);
+      }
+    }
+    EPI_STAMP(2);
+    if (simple) {
+      if (has_bias) {
+        // the 32 bias values of this chunk: one coalesced load, staged in a 128-byte per-warp slot and
+        // read back as 8 broadcast float4 (32 dependent register shuffles cost ~1000 cycles per chunk)
+        const int nb = n0 + c0 + lane;
+        const float bl = (nb < n_end) ? __ldg(bias + nb) : 0.0f;
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_slot + (uint32_t)lane * 4u), "f"(bl) : "memory");
+        __syncwarp();
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          float b[4];
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b[0]), "=f"(b[1]), "=f"(b[2]), "=f"(b[3])
+                       : "r"(bias_slot + (uint32_t)g * 16u));
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            r[4 * g + e] = __float_as_uint(epi_value<ACT, DACT>(alpha, beta, true, false, __uint_as_float(r[4 * g + e]), b[e], 1.0f, 0.0f));
+        }
+        __syncwarp();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          r[j] = __float_as_uint(epi_value<ACT, DACT>(alpha, beta, false, false, __uint_as_float(r[j]), 0.0f, 1.0f, 0.0f));
       }
     }
     // 32x32 tile -> shared memory, 16-byte groups XOR-swizzled by the row (= TMA SWIZZLE_128B, and
@@ -183,6 +244,7 @@ __device__ __noinline__ void epilogue_tile(const TcParams &p, const CUtensorMap 
     for (int g = 0; g < 8; ++g)
       asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(buf + (uint32_t)lane * 128u + (uint32_t)((g ^ (lane & 7)) << 4)),
                    "r"(r[4 * g]), "r"(r[4 * g + 1]), "r"(r[4 * g + 2]), "r"(r[4 * g + 3]) : "memory");
+    EPI_STAMP(3);
     if (!simple) {
       __syncwarp();
       // row-contiguous domain: 8 lanes cover the 128 bytes of one row, global accesses coalesce
@@ -191,44 +253,47 @@ __device__ __noinline__ void epilogue_tile(const TcParams &p, const CUtensorMap 
       if (has_bias) {
 #pragma unroll
         for (int e = 0; e < 4; ++e)
-          if (n + e < n_end) bv[e] = __ldg(p.ep.bias + n + e);
+          if (n + e < n_end) bv[e] = __ldg(bias + n + e);
       }
-#pragma unroll 2
+      const bool full4 = n + 4 <= n_end;
+      // all global reads of the chunk are issued before the first use (8 independent 16-byte loads per lane)
+      // (one source per epilogue kind: the derivative source for data gradients, old C for beta != 0)
+      const bool pre = full4 && d_vec && c_vec && (has_d != has_c);
+      float4 gq[8];
+      if (pre) {
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int m = m_base + it * 4 + (lane >> 3);
+          if (m < M)
+            gq[it] = has_d ? __ldg(reinterpret_cast<const float4 *>(dsrc + (size_t)m * ld_dsrc + n))
+                           : *reinterpret_cast<const float4 *>(C + (size_t)m * ldc + n);
+        }
+      }
+#pragma unroll
       for (int it = 0; it < 8; ++it) {
         const int row = it * 4 + (lane >> 3);
         const uint32_t saddr = buf + (uint32_t)row * 128u + (uint32_t)((cg ^ (row & 7)) << 4);
         float v[4];
-        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3])
-                     : "r"(saddr) : "memory");
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(saddr));
         const int m = m_base + row;
-        if (m >= p.M || n >= n_end) continue;
-        float *cp = p.C + (size_t)m * p.ldc + n;
-        const float *dp = p.ep.dsrc + (size_t)m * p.ep.ld_dsrc + n;
-        const bool full4 = n + 4 <= n_end;
+        if (m >= M || n >= n_end) continue;
+        float *cp = C + (size_t)m * ldc + n;
+        const float *dp = dsrc + (size_t)m * ld_dsrc + n;
         float d[4] = {1.0f, 1.0f, 1.0f, 1.0f}, c[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-        if (has_d) {
-          if (full4 && d_vec) {
-            const float4 t = __ldg(reinterpret_cast<const float4 *>(dp));
-            d[0] = t.x; d[1] = t.y; d[2] = t.z; d[3] = t.w;
-          } else {
+        if (pre) {
+          if (has_d) { d[0] = gq[it].x; d[1] = gq[it].y; d[2] = gq[it].z; d[3] = gq[it].w; }
+          else { c[0] = gq[it].x; c[1] = gq[it].y; c[2] = gq[it].z; c[3] = gq[it].w; }
+        } else {
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
-              if (n + e < n_end) d[e] = __ldg(dp + e);
-          }
-        }
-        if (has_c) {
-          if (full4 && c_vec) {
-            const float4 t = *reinterpret_cast<const float4 *>(cp);
-            c[0] = t.x; c[1] = t.y; c[2] = t.z; c[3] = t.w;
-          } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-              if (n + e < n_end) c[e] = cp[e];
-          }
+          for (int e = 0; e < 4; ++e)
+            if (n + e < n_end) {
+              if (has_d) d[e] = __ldg(dp + e);
+              if (has_c) c[e] = cp[e];
+            }
         }
 #pragma unroll
-        for (int e = 0; e < 4; ++e) v[e] = epi_value<ACT, DACT>(p.ep, has_bias, has_c, v[e], bv[e], d[e], c[e]);
-        if (p.tma_store) {
+        for (int e = 0; e < 4; ++e) v[e] = epi_value<ACT, DACT>(alpha, beta, has_bias, has_c, v[e], bv[e], d[e], c[e]);
+        if (tma_store) {
           asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
         } else if (full4 && c_vec) {
           *reinterpret_cast<float4 *>(cp) = make_float4(v[0], v[1], v[2], v[3]);
@@ -239,14 +304,19 @@ __device__ __noinline__ void epilogue_tile(const TcParams &p, const CUtensorMap 
         }
       }
     }
-    if (p.tma_store) {
+    EPI_STAMP(4);
+    if (tma_store) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the TMA
       __syncwarp();
       if (lane == 0) tma_store_2d(map_c, buf, n0 + c0, m_base);      // rows/columns past M/N are clipped
     } else {
       __syncwarp();
     }
+    EPI_STAMP(5);
   }
+#undef EPI_STAMP
+  if (timing)
+    for (int i = 0; i < 6; ++i) p.stamps[16 * blockIdx.x + 8 + i] += tacc[i];
 }
 
 template <bool A_KMAJOR, bool B_KMAJOR>
@@ -267,11 +337,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const uint32_t tmem_slot = bars + 8 * (2 * MAX_STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  long long *stamp = p.stamps ? p.stamps + 8 * blockIdx.x : nullptr;
+  long long *stamp = p.stamps ? p.stamps + 16 * blockIdx.x : nullptr;
   if (stamp && threadIdx.x == 0) stamp[0] = clock64();
   const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + p.BN - 1) / p.BN;
   const int num_tiles = tiles_m * tiles_n;
   const int num_k = (p.K + BK - 1) / BK;
+  // split-K pair: CTA rank r of the cluster contracts k-blocks [kb_lo, kb_hi) of tile blockIdx.x/2
+  const uint32_t crank = (p.splitk == 2) ? cluster_ctarank() : 0u;
+  const int kb_half = (num_k + 1) >> 1;
+  const int kb_lo = (p.splitk == 2 && crank == 1) ? kb_half : 0;
+  const int kb_hi = (p.splitk == 2 && crank == 0) ? kb_half : num_k;
+  const int tile_first = (p.splitk == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = (p.splitk == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
@@ -297,9 +374,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       (void)staging;
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
         const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * p.BN;
-        for (int kb = 0; kb < num_k; ++kb) {
+        for (int kb = kb_lo; kb < kb_hi; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_BYTES;
           mbar_expect_tx(full_bar(stage), stage_tx);
@@ -315,7 +392,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           } else {
             for (int j = 0; j < (p.BN + 31) / 32; ++j) tma_load_2d(sb + j * 4096, &map_b, full_bar(stage), n0 + 32 * j, k0);
           }
-          if (stamp && kb == 0 && tile == (int)blockIdx.x) stamp[2] = clock64();
+          if (stamp && kb == kb_lo && tile == tile_first) stamp[2] = clock64();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -326,22 +403,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+      for (int tile = tile_first; tile < num_tiles; tile += tile_step, ++local) {
         const int acc = local & 1;
         const uint32_t acc_phase = (uint32_t)(local >> 1) & 1;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);   // epilogue drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)acc * MAX_BN;
-        for (int kb = 0; kb < num_k; ++kb) {
+        for (int kb = kb_lo; kb < kb_hi; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          if (stamp && kb == 0 && local == 0) stamp[3] = clock64();
+          if (stamp && kb == kb_lo && local == 0) stamp[3] = clock64();
           const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t ad = make_desc(sa + k * p.a_kstep, p.a_lbo, p.a_sbo, p.a_layout);
             const uint64_t bd = make_desc(sb + k * p.b_kstep, p.b_lbo, p.b_sbo, p.b_layout);
-            umma_tf32(tmem_d, ad, bd, p.idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_tf32(tmem_d, ad, bd, p.idesc, (kb != kb_lo || k != 0) ? 1u : 0u);
           }
           umma_commit(empty_bar(stage));             // frees the smem slot when these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -355,29 +432,61 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int quad = warp & 3;                        // TMEM lanes [32*quad, 32*quad+32)
     int local = 0;
     int chunk = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+    for (int tile = tile_first; tile < num_tiles; tile += tile_step, ++local) {
       const int acc = local & 1;
       const uint32_t acc_phase = (uint32_t)(local >> 1) & 1;
       const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * p.BN;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       if (stamp && threadIdx.x == 64) stamp[5] = clock64();
+      int c_begin = 0, c_end = p.BN;
+      uint32_t recv = 0;
+      if (p.splitk == 2) {
+        // Exchange: this CTA finishes columns [c_begin, c_end) of the tile and ships its partial sums of
+        // the other half to the peer.  The receive area is the (now idle) operand ring of the peer,
+        // which is only safe to overwrite once the peer's MMAs have retired: cluster barrier #1.
+        const int half = ((p.BN >> 5) + 1) >> 1 << 5;         // columns owned by rank 0 (multiple of 32)
+        c_begin = crank ? half : 0;
+        c_end = crank ? p.BN : half;
+        const int s_begin = crank ? 0 : half, s_end = crank ? half : p.BN;
+        const int peer_chunks = (s_end - s_begin) >> 5, own_chunks = (c_end - c_begin + 31) >> 5;
+        __syncwarp();
+        cluster_arrive();
+        cluster_wait();
+        const uint32_t taddr_s = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * MAX_BN;
+        const uint32_t remote = mapa_shared(smem_base + (uint32_t)(quad * peer_chunks) * 4096u, crank ^ 1u);
+        for (int c0 = s_begin; c0 < s_end; c0 += 32) {
+          if (n0 + c0 >= p.N) break;
+          uint32_t r[32];
+          tmem_ld32(taddr_s + c0, r);
+          const uint32_t dst = remote + (uint32_t)((c0 - s_begin) >> 5) * 4096u + (uint32_t)lane * 128u;
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (uint32_t)((g ^ (lane & 7)) << 4)),
+                         "r"(r[4 * g]), "r"(r[4 * g + 1]), "r"(r[4 * g + 2]), "r"(r[4 * g + 3]) : "memory");
+        }
+        __syncwarp();
+        cluster_arrive();       // release: the stores above are visible to the peer after its wait
+        cluster_wait();
+        recv = smem_base + (uint32_t)(quad * own_chunks) * 4096u;
+      }
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * MAX_BN;
       const uint32_t stg = staging + (uint32_t)(warp - 2) * 8192u;
+      const uint32_t bias_slot = bars + 256u + (uint32_t)(warp - 2) * 128u;
       // the activation / derivative kind is a compile-time constant inside each instantiation: a run-time
       // switch per element made the unrolled epilogue ~4500 instructions per 32-column chunk
       if (p.ep.dact != B200_ACT_NONE) {
         switch (p.ep.dact) {
-          case B200_ACT_LOGISTIC: epilogue_tile<B200_ACT_NONE, B200_ACT_LOGISTIC>(p, &map_c, taddr, stg, m0 + quad * 32, n0, lane, chunk); break;
-          case B200_ACT_TANH: epilogue_tile<B200_ACT_NONE, B200_ACT_TANH>(p, &map_c, taddr, stg, m0 + quad * 32, n0, lane, chunk); break;
-          default: epilogue_tile<B200_ACT_NONE, B200_ACT_RELU>(p, &map_c, taddr, stg, m0 + quad * 32, n0, lane, chunk); break;
+          case B200_ACT_LOGISTIC: epilogue_tile<B200_ACT_NONE, B200_ACT_LOGISTIC>(p, &map_c, taddr, stg, m0 + quad * 32, n0, lane, chunk, c_begin, c_end, recv, bias_slot); break;
+          case B200_ACT_TANH: epilogue_tile<B200_ACT_NONE, B200_ACT_TANH>(p, &map_c, taddr, stg, m0 + quad * 32, n0, lane, chunk, c_begin, c_end, recv, bias_slot); break;
+          default: epilogue_tile<B200_ACT_NONE, B200_ACT_RELU>(p, &map_c, taddr, stg, m0 + quad * 32, n0, lane, chunk, c_begin, c_end, recv, bias_slot); break;
         }
       } else {
         switch (p.ep.act) {
-          case B200_ACT_LOGISTIC: epilogue_tile<B200_ACT_LOGISTIC, B200_ACT_NONE>(p, &map_c, taddr, stg, m0 + quad * 32, n0, lane, chunk); break;
-          case B200_ACT_TANH: epilogue_tile<B200_ACT_TANH, B200_ACT_NONE>(p, &map_c, taddr, stg, m0 + quad * 32, n0, lane, chunk); break;
-          case B200_ACT_RELU: epilogue_tile<B200_ACT_RELU, B200_ACT_NONE>(p, &map_c, taddr, stg, m0 + quad * 32, n0, lane, chunk); break;
-          default: epilogue_tile<B200_ACT_NONE, B200_ACT_NONE>(p, &map_c, taddr, stg, m0 + quad * 32, n0, lane, chunk); break;
+          case B200_ACT_LOGISTIC: epilogue_tile<B200_ACT_LOGISTIC, B200_ACT_NONE>(p, &map_c, taddr, stg, m0 + quad * 32, n0, lane, chunk, c_begin, c_end, recv, bias_slot); break;
+          case B200_ACT_TANH: epilogue_tile<B200_ACT_TANH, B200_ACT_NONE>(p, &map_c, taddr, stg, m0 + quad * 32, n0, lane, chunk, c_begin, c_end, recv, bias_slot); break;
+          case B200_ACT_RELU: epilogue_tile<B200_ACT_RELU, B200_ACT_NONE>(p, &map_c, taddr, stg, m0 + quad * 32, n0, lane, chunk, c_begin, c_end, recv, bias_slot); break;
+          default: epilogue_tile<B200_ACT_NONE, B200_ACT_NONE>(p, &map_c, taddr, stg, m0 + quad * 32, n0, lane, chunk, c_begin, c_end, recv, bias_slot); break;
         }
       }
       tc_fence_before();
@@ -385,6 +494,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       if (stamp && threadIdx.x == 64) stamp[6] = clock64();
     }
     if (p.tma_store && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+  if (warp < 2 && p.splitk == 2) {
+    // producer / MMA warps only take part in the two cluster barriers of the exchange
+    __syncwarp();
+    cluster_arrive();
+    cluster_wait();
+    cluster_arrive();
+    cluster_wait();
   }
 
   tc_fence_before();
@@ -465,27 +582,38 @@ int get_map(b200_ctx *ctx, TcState *s, const float *ptr, uint64_t d0, uint64_t d
   return B200_OK;
 }
 
-int pick_bn(int M, int N, int K, int sm_count) {
-  // Measured on B200 (tools/gemm_stamps.py): one kind::tf32 M=128 instruction costs ~150 cycles for every
-  // N <= 256 (the A read from shared memory is the floor), so a 32-wide k-block costs >= ~610 cycles per
-  // CTA whatever the tile width; when many CTAs stream at once the L2->SM fabric (~7.3 KB/cycle for the
-  // whole chip) becomes the bound instead.  Pick the N tile (multiple of 32, or 16 for N <= 16) that
-  // minimises   waves * k-blocks * max(610, active*(16 KiB + 128 B * BN)/7300)  +  exposed epilogue.
-  if (N <= 16) return 16;
+// Tile width and split-K decision.
+// Measured on B200 (tools/gemm_stamps.py): one kind::tf32 M=128 instruction costs ~150 cycles for every
+// N <= 256 (the A read from shared memory is the floor), so a 32-wide k-block costs >= ~610 cycles per
+// CTA whatever the tile width; when many CTAs stream at once the L2->SM fabric (~7.3 KB/cycle for the
+// whole chip) becomes the bound instead.  Candidates: N tile in {32..256 step 32} (16 for N <= 16),
+// alone or as a split-K pair (two CTAs per tile, half of K each, partials exchanged through distributed
+// shared memory) when that fits in one wave.  Cost in cycles:
+//   waves * k-blocks * max(610, active*(16 KiB + 128 B * BN)/7300) + exposed epilogue (+ exchange).
+void pick_tile(int M, int N, int K, int sm_count, bool allow_split, int *bn_out, int *split_out) {
+  *split_out = 1;
+  if (N <= 16) { *bn_out = 16; return; }
   const int tiles_m = (M + BM - 1) / BM;
-  const double num_k = (double)((K + BK - 1) / BK);
-  int best = 32;
+  const int num_k = (K + BK - 1) / BK;
+  int best = 32, best_split = 1;
   double best_cost = 1e30;
   for (int bn = 256; bn >= 32; bn -= 32) {
     const int tn = (N + bn - 1) / bn;
     const long tiles = (long)tiles_m * tn;
-    const long waves = (tiles + sm_count - 1) / sm_count;
-    const double active = (double)(tiles < sm_count ? tiles : sm_count);
-    const double kblock = fmax(610.0, active * (16384.0 + 128.0 * bn) / 7300.0);
-    const double cost = (double)waves * num_k * kblock + (bn / 32) * 500.0;
-    if (cost < best_cost - 1e-6) { best_cost = cost; best = bn; }
+    for (int split = 1; split <= 2; ++split) {
+      if (split == 2 && (!allow_split || 2 * tiles > sm_count || num_k < 8)) continue;
+      const long ctas = tiles * split;
+      const long waves = (ctas + sm_count - 1) / sm_count;
+      const double active = (double)(ctas < sm_count ? ctas : sm_count);
+      const double kblock = fmax(610.0, active * (16384.0 + 128.0 * bn) / 7300.0);
+      const double kblocks = (split == 2) ? (double)((num_k + 1) / 2) : (double)num_k;
+      double cost = (double)waves * kblocks * kblock + (bn / 32) * 500.0 / split;
+      if (split == 2) cost += 1500.0 + (bn / 64) * 450.0;   // two cluster barriers + DSMEM exchange of half a tile
+      if (cost < best_cost - 1e-6) { best_cost = cost; best = bn; best_split = split; }
+    }
   }
-  return best;
+  *bn_out = best;
+  *split_out = best_split;
 }
 
 template <bool AK, bool BKM>
@@ -497,6 +625,23 @@ int launch(b200_ctx *ctx, TcState *s, int idx, const CUtensorMap &ma, const CUte
     s->attr_set[idx] = true;
   }
   const size_t smem = (size_t)p.stages * p.stage_bytes + SMEM_EXTRA;
+  if (p.splitk == 2) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(NTHREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ma, mb, mc, p));
+    LAUNCH_CHECK(ctx);
+    return B200_OK;
+  }
   kern<<<grid, NTHREADS, smem, ctx->stream>>>(ma, mb, mc, p);
   LAUNCH_CHECK(ctx);
   return B200_OK;
@@ -544,7 +689,11 @@ int gemm_tc(b200_ctx *ctx, int transA, int transB, int M, int N, int K, const fl
 
   TcParams p;
   p.M = M; p.N = N; p.K = K;
-  p.BN = s->force_bn ? s->force_bn : pick_bn(M, N, K, ctx->sm_count);
+  pick_tile(M, N, K, ctx->sm_count, !(s->dbg_flags & 16), &p.BN, &p.splitk);
+  if (s->force_bn) {
+    p.BN = s->force_bn & 0xfff;
+    p.splitk = (s->force_bn & 0x1000) ? 2 : 1;
+  }
   // the ring is as deep as shared memory allows: loads are latency/bandwidth bound, so bytes in flight matter
   p.stage_bytes = (uint32_t)A_BYTES + (b_k ? (uint32_t)p.BN * BK * 4 : (uint32_t)((p.BN + 31) / 32) * 4096u);
   p.stages = (SMEM_MAX - SMEM_EXTRA) / (int)p.stage_bytes;
@@ -589,7 +738,10 @@ int gemm_tc(b200_ctx *ctx, int transA, int transB, int M, int N, int K, const fl
   }
 
   const int tiles = ((M + BM - 1) / BM) * tiles_n;
-  const int grid = tiles < ctx->sm_count ? tiles : ctx->sm_count;
+  if (p.splitk == 2 && (2 * tiles > ctx->sm_count || (p.BN & 31) != 0 || (K + BK - 1) / BK < 2)) p.splitk = 1;
+  // the exchange area of a split-K pair (half a tile per CTA) lives in the operand ring
+  if (p.splitk == 2 && (size_t)p.stages * p.stage_bytes < (size_t)(p.BN / 2 + 32) * 512u) p.splitk = 1;
+  const int grid = p.splitk == 2 ? 2 * tiles : (tiles < ctx->sm_count ? tiles : ctx->sm_count);
   if (a_k && b_k) return launch<true, true>(ctx, s, 0, ma, mb, mc, p, grid);
   if (a_k && !b_k) return launch<true, false>(ctx, s, 1, ma, mb, mc, p, grid);
   if (!a_k && b_k) return launch<false, true>(ctx, s, 2, ma, mb, mc, p, grid);

@@ -26,7 +26,7 @@ for a in sys.argv[1:]:
     A = DeviceArray.from_numpy(ctx, rng.uniform(-1, 1, (K, M) if ta else (M, K)).astype(np.float32))
     B = DeviceArray.from_numpy(ctx, rng.uniform(-1, 1, (N, K) if tb else (K, N)).astype(np.float32))
     Cm = DeviceArray(ctx, (M, N))
-    st = DeviceArray(ctx, (148 * 8,), np.int64)
+    st = DeviceArray(ctx, (148 * 16,), np.int64)
 
     def launch():
         check(lib.b200_sgemm(ctx.h, C.c_int(ta), C.c_int(tb), C.c_int(M), C.c_int(N), C.c_int(K), C.c_float(1.0),
@@ -37,9 +37,13 @@ for a in sys.argv[1:]:
     check(lib.b200_debug_tc_stamps(ctx.h, st.ptr))
     launch()
     check(lib.b200_debug_tc_stamps(ctx.h, None))
-    s = st.numpy().reshape(148, 8)
-    s = s[s[:, 0] != 0]
+    s16 = st.numpy().reshape(148, 16)
+    s16 = s16[s16[:, 0] != 0]
+    s = s16[:, :8]
     rel = (s[:, 1:] - s[:, :1]).astype(np.float64)
     print("case %s: %d CTAs; cycles since CTA start (median / max over CTAs)" % (a, len(s)))
     for i, n in enumerate(names):
         print("   %-16s %9.0f %9.0f" % (n, np.median(rel[:, i]), rel[:, i].max()))
+    en = ["wait staging buf", "tcgen05.ld", "split-K addend", "math + st.shared", "transposed pass", "fence + TMA issue"]
+    print("   epilogue warp 2, cycles summed over its chunks (median over CTAs): " +
+          ", ".join("%s %.0f" % (n, np.median(s16[:, 8 + i])) for i, n in enumerate(en)))
