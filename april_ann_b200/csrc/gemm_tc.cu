@@ -65,6 +65,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
       "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, uint32_t src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0),
                "r"(c1)
@@ -381,17 +387,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_BYTES;
           mbar_expect_tx(full_bar(stage), stage_tx);
           const int k0 = kb * BK;
-          if (A_KMAJOR) {
-            tma_load_2d(sa, &map_a, full_bar(stage), k0, m0);                        // box {32 k, 128 rows}
-          } else {
-#pragma unroll
-            for (int j = 0; j < BM / 32; ++j) tma_load_2d(sa + j * 4096, &map_a, full_bar(stage), m0 + 32 * j, k0);
-          }
-          if (B_KMAJOR) {
-            tma_load_2d(sb, &map_b, full_bar(stage), k0, n0);                        // box {32 k, BN rows}
-          } else {
-            for (int j = 0; j < (p.BN + 31) / 32; ++j) tma_load_2d(sb + j * 4096, &map_b, full_bar(stage), n0 + 32 * j, k0);
-          }
+          // one TMA per operand per stage.  MN-major operands are described as 3-D tensors
+          // {32 contiguous elements, K rows, MN/32 chunks}: a box {32, 32, tile/32} lands as consecutive
+          // 4 KiB [32 k][32 mn] blocks, the layout the MN-major UMMA descriptor walks (LBO = 4 KiB).
+          // (issuing the 4 + 8 separate 4 KiB boxes of a 128x256 tile cost ~100 cycles each and made the
+          // weight-gradient main loop TMA-issue bound: 1150 instead of 610 cycles per k-block)
+          if (A_KMAJOR) tma_load_2d(sa, &map_a, full_bar(stage), k0, m0);            // box {32 k, 128 rows}
+          else tma_load_3d(sa, &map_a, full_bar(stage), 0, k0, m0 >> 5);             // box {32 m, 32 k, 4}
+          if (B_KMAJOR) tma_load_2d(sb, &map_b, full_bar(stage), k0, n0);            // box {32 k, BN rows}
+          else tma_load_3d(sb, &map_b, full_bar(stage), 0, k0, n0 >> 5);             // box {32 n, 32 k, BN/32}
           if (stamp && kb == kb_lo && tile == tile_first) stamp[2] = clock64();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -582,6 +586,35 @@ int get_map(b200_ctx *ctx, TcState *s, const float *ptr, uint64_t d0, uint64_t d
   return B200_OK;
 }
 
+// 3-D fp32 tensor map of an MN-major operand stored as [K rows][MN contiguous], row pitch ld floats:
+// dim0 = 32 elements inside a chunk, dim1 = K rows, dim2 = MN/32 chunks (128 bytes apart).  The last chunk
+// may run past MN: what it reads there (the row tail / the next row; the pool pads every block by 512 B)
+// only reaches accumulator rows/columns >= M/N, which the epilogue never stores.  K is bounded exactly, so
+// the contraction tail is zero-filled.
+int get_map_mn(b200_ctx *ctx, TcState *s, const float *ptr, uint64_t mn, uint64_t k, uint64_t ld, uint32_t chunks_per_box,
+               CUtensorMap *out) {
+  MapKey key{ptr, mn, k, ld, 0x80000000u | chunks_per_box, 32, (uint32_t)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B};
+  auto it = s->maps.find(key);
+  if (it != s->maps.end()) { *out = it->second; return B200_OK; }
+  cuuint64_t gdim[3] = {32, k, (mn + 31) / 32};
+  cuuint64_t gstride[2] = {ld * sizeof(float), 128};
+  cuuint32_t box[3] = {32, BK, chunks_per_box};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUtensorMap m;
+  CUresult r = s->encode(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)ptr, gdim, gstride, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    b200_set_error("cuTensorMapEncodeTiled (3-D, MN-major) failed (%d) for mn %llu k %llu ld %llu box {32,32,%u}", (int)r,
+                   (unsigned long long)mn, (unsigned long long)k, (unsigned long long)ld, chunks_per_box);
+    return B200_ERR_CUDA;
+  }
+  if (s->maps.size() > 4096) s->maps.clear();
+  s->maps.emplace(key, m);
+  *out = m;
+  return B200_OK;
+}
+
 // Tile width and split-K decision.
 // Measured on B200 (tools/gemm_stamps.py): one kind::tf32 M=128 instruction costs ~150 cycles for every
 // N <= 256 (the A read from shared memory is the floor), so a 32-wide k-block costs >= ~610 cycles per
@@ -721,10 +754,10 @@ int gemm_tc(b200_ctx *ctx, int transA, int transB, int M, int N, int K, const fl
   CUtensorMap ma, mb;
   int st;
   if (a_k) st = get_map(ctx, s, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, BM, CU_TENSOR_MAP_SWIZZLE_128B, &ma);
-  else st = get_map(ctx, s, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, &ma);
+  else st = get_map_mn(ctx, s, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM / 32, &ma);
   if (st) return st;
   if (b_k) st = get_map(ctx, s, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK, (uint32_t)p.BN, CU_TENSOR_MAP_SWIZZLE_128B, &mb);
-  else st = get_map(ctx, s, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, &mb);
+  else st = get_map_mn(ctx, s, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, (uint32_t)((p.BN + 31) / 32), &mb);
   if (st) return st;
 
   // C goes out through TMA stores of 32x32 boxes when its layout allows (16-byte aligned base and pitch);
