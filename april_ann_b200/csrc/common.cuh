@@ -18,7 +18,17 @@ struct b200_ctx {
   int device = 0;
   int sm_count = 148;
   int math_mode = B200_MATH_FP32;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;          // the stream kernels are launched on (main, or a side branch)
+  cudaStream_t main_stream = nullptr;
+  // side branches: independent work of a step (weight gradients, per-tensor SGD, loss statistics)
+  // runs beside the critical path; captured into the step's CUDA graph as parallel branches
+  static constexpr int kBranches = 3;
+  cudaStream_t side_stream[kBranches] = {};
+  cudaEvent_t ev_fork[kBranches] = {}, ev_side[kBranches] = {};
+  bool side_open[kBranches] = {};
+  int cur_branch = -1;                    // -1: main
+  int sm_budget = 0;                      // SMs a persistent contraction may plan for (0: all)
+  std::vector<std::pair<size_t, void *>> deferred_free;   // blocks released while branches are open
   cudaStream_t comm_stream = nullptr;
   cudaEvent_t ev_compute = nullptr, ev_comm = nullptr;
   cudaEvent_t ev_bucket[16] = {};        // completion of the async gradient buckets
@@ -28,8 +38,8 @@ struct b200_ctx {
   std::map<void *, size_t> live_blocks;
   std::mutex mu;
   // scratch for reductions / split-K etc.
-  void *scratch = nullptr;
-  size_t scratch_bytes = 0;
+  void *scratch[kBranches + 1] = {};      // one per branch (+ main): concurrent branches must not share it
+  size_t scratch_bytes[kBranches + 1] = {};
   // NCCL (dlopen'ed lazily)
   void *nccl_comm = nullptr;
   int nranks = 1, rank = 0;
@@ -52,6 +62,19 @@ void *b200_scratch(b200_ctx *ctx, size_t bytes);
     (ctx)->launches++;                                                        \
     int _st = b200_check_cuda(cudaGetLastError(), "kernel launch", __FILE__, __LINE__); \
     if (_st) return _st;                                                      \
+  } while (0)
+
+// Kernels that run beside a contraction CTA inside a step (side branches) ask for the same shared-memory
+// carve-out as the contraction (maximum shared memory): CTAs of kernels with different carve-outs are not
+// co-scheduled on one SM, and with the default preference these kernels only got the SMs a contraction
+// left idle.  Call once per kernel, before its launch.
+#define PREFER_MAX_SMEM_ONCE(kernel)                                                                          \
+  do {                                                                                                        \
+    static bool _done = false;                                                                                \
+    if (!_done) {                                                                                             \
+      cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); \
+      _done = true;                                                                                           \
+    }                                                                                                         \
   } while (0)
 
 #define ARG_CHECK(cond, msg)                                                  \

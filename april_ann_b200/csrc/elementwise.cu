@@ -230,6 +230,7 @@ extern "C" int b200_bias_grad(b200_ctx *ctx, int M, int N, const float *dy, int 
 }
 extern "C" int b200_loss_accumulate(b200_ctx *ctx, int M, const float *loss_rows, double *stats) {
   ARG_CHECK(ctx && loss_rows && stats, "NULL pointer");
+  PREFER_MAX_SMEM_ONCE(loss_accumulate_kernel);
   loss_accumulate_kernel<<<1, 256, 0, ctx->stream>>>(M, loss_rows, stats);
   LAUNCH_CHECK(ctx);
   return B200_OK;

@@ -28,11 +28,21 @@ constexpr int UMMA_K = 8;        // tf32: 32 bytes of K per instruction
 constexpr int MAX_STAGES = 8;
 constexpr int MAX_BN = 256;
 constexpr int A_BYTES = BM * BK * 4;          // 16 KiB
-constexpr int STAGING_BYTES = 4 * 2 * 32 * 32 * 4;   // two 32x32 fp32 staging buffers per epilogue warp
-constexpr int SMEM_EXTRA = STAGING_BYTES + 256 /*barriers*/ + 512 /*per-warp bias slots*/ + 1024 /*align slack*/;
+constexpr int EPI_WARPS = 8;         // two per TMEM lane quadrant, each takes half of the tile's column chunks
+// Staging for the TMA stores.  On the last tile of a CTA (the only one at the BASELINE MLP sizes) the operand
+// ring is idle once the accumulator is complete and every epilogue warp stages there; on earlier tiles of a
+// persistent CTA the ring is busy with the next tile's loads, the epilogue is hidden behind that main loop,
+// and one warp per quadrant works through a dedicated 4 KiB buffer.  Keeping the dedicated part small leaves
+// ~16 KiB of shared memory per SM, so the light kernels of a training step (SGD, bias gradients, loss
+// statistics) can be co-resident with a contraction CTA instead of waiting for it.
+constexpr int STAGING_BYTES = 4 * 4096;
+constexpr int BIAS_BYTES = MAX_BN * 4;               // the tile's slice of the bias vector
+constexpr int SMEM_EXTRA = STAGING_BYTES + 256 /*barriers*/ + BIAS_BYTES + 1024 /*align slack*/;
 constexpr int SMEM_MAX = 227 * 1024;
-constexpr int NTHREADS = 192;
+constexpr int SMEM_BUDGET = 211 * 1024;   // ring + extras: four 48 KiB stages of a 128x256 tile, ~16 KiB per SM left for co-resident kernels
+constexpr int NTHREADS = 64 + 32 * EPI_WARPS;        // warp 0 producer, warp 1 MMA issuer, warps 2..9 epilogue
 constexpr int TMEM_COLS = 512;   // two 256-column accumulator stages
+constexpr int STAMP_STRIDE = 32;  // bring-up: int64 stamps per CTA
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -125,6 +135,32 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
+__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
+// arrive on an mbarrier of another CTA of the cluster (address from mapa), releasing this thread's
+// earlier (remote) stores at cluster scope
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// bulk copy shared::cta -> shared memory of another CTA of the cluster, completion counted in bytes on an
+// mbarrier of the destination CTA
+__device__ __forceinline__ void dsm_bulk_copy(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t bar_cluster) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_cluster),
+               "r"(src_cta), "r"(bytes), "r"(bar_cluster)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "WAIT_LOOP_C:\n"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE_C;\n"
+      "bra WAIT_LOOP_C;\n"
+      "DONE_C:\n"
+      "}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 
@@ -150,7 +186,7 @@ struct TcParams {
   int splitk;          // 1, or 2: a cluster of two CTAs shares one output tile, each contracting half of K;
                        //          the partial accumulators meet through distributed shared memory
   int tma_store;       // 1: the epilogue writes C through map_c (cp.async.bulk.tensor store), 0: direct stores
-  uint32_t dbg_flags;  // bring-up only: 8 = force direct stores instead of TMA stores, 16 = no split-K
+  uint32_t dbg_flags;  // bring-up only: 8 = force direct stores instead of TMA stores, 16 = no split-K, 32 = epilogue phase clocks
   long long *stamps;   // bring-up only: per-CTA clock64 stamps [grid][16] (nullptr in production)
 };
 
@@ -166,24 +202,41 @@ __device__ __forceinline__ float epi_value(float alpha, float beta, bool has_bia
   return v;
 }
 
-// Epilogue of one 128 x BN accumulator for one warp (32 TMEM lanes = 32 rows starting at m_base):
-// tcgen05.ld 32 columns at a time -> shared memory (transpose) -> global through a TMA store, or
-// direct row-contiguous stores when C cannot be described by a tensor map.
+__device__ __forceinline__ void bulk_wait_read(int pending) {
+  // cp.async.bulk.wait_group.read takes an immediate
+  switch (pending) {
+    case 0: asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); break;
+    case 1: asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); break;
+    case 2: asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory"); break;
+    default: asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory"); break;
+  }
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory"); }
+
+// staging buffers of one epilogue warp: `nbuf` 4 KiB tiles, `stride` bytes apart
+struct Staging {
+  uint32_t base, stride;
+  int nbuf;
+  __device__ __forceinline__ uint32_t buf(int j) const { return base + (uint32_t)j * stride; }
+};
+
+// Epilogue of the columns [c_begin, c_end) of one 128 x BN accumulator for one warp (32 TMEM lanes = 32 rows
+// starting at m_base): tcgen05.ld 32 columns at a time -> shared memory (transpose) -> global through a TMA
+// store, or direct row-contiguous stores when C cannot be described by a tensor map.
 // Every field of the parameter block is copied into a register up front: left in the struct they
 // were re-read from local memory for every element (ptxas kept a stack copy of the kernel parameters).
 template <int ACT, int DACT>
-__device__ __forceinline__ void epilogue_tile(const TcParams &p, const CUtensorMap *map_c, uint32_t taddr, uint32_t stg,
-                                              int m_base, int n0, int lane, int &chunk, int c_begin, int c_end,
-                                              uint32_t recv, uint32_t bias_slot) {
+__device__ __forceinline__ void epilogue_tile(const TcParams &p, const CUtensorMap *map_c, uint32_t taddr, const Staging &stg,
+                                              int m_base, int n0, int lane, int &issued, int c_begin, int c_end,
+                                              uint32_t recv, uint32_t bias_smem) {
   const float alpha = p.ep.alpha, beta = p.ep.beta;
-  const float *__restrict__ bias = p.ep.bias;
   const float *__restrict__ dsrc = p.ep.dsrc;
   const int ld_dsrc = p.ep.ld_dsrc, ldc = p.ldc, M = p.M;
   float *__restrict__ C = p.C;
   const bool tma_store = p.tma_store != 0;
   const int n_end = min(p.N, n0 + p.BN);
   const int cg = lane & 7;                       // 16-byte column group this lane handles after the transpose
-  const bool has_bias = bias != nullptr, has_c = beta != 0.0f;
+  const bool has_bias = p.ep.bias != nullptr, has_c = beta != 0.0f;
   constexpr bool has_d = DACT != B200_ACT_NONE;
   const bool c_vec = ((ldc & 3) == 0) && ((((uintptr_t)C) & 15) == 0);
   const bool d_vec = !has_d || (((ld_dsrc & 3) == 0) && ((((uintptr_t)dsrc) & 15) == 0));
@@ -191,22 +244,26 @@ __device__ __forceinline__ void epilogue_tile(const TcParams &p, const CUtensorM
   // the ones that read global memory per element (derivative source, old C) run after the transpose
   const bool simple = tma_store && !has_d && !has_c;
   // bring-up: phase durations of warp 2 lane 0, accumulated in registers, flushed once at the end
-  const bool timing = p.stamps != nullptr && threadIdx.x == 64;
+  const bool timing = p.stamps != nullptr && (p.dbg_flags & 32u) && threadIdx.x == 64;   // per-phase clocks perturb the epilogue: opt-in
   long long tacc[6] = {0, 0, 0, 0, 0, 0};
   long long tq = timing ? clock64() : 0;
 #define EPI_STAMP(i) do { if (timing) { const long long tn = clock64(); tacc[i] += tn - tq; tq = tn; } } while (0)
-  for (int c0 = c_begin; c0 < c_end; c0 += 32, ++chunk) {
-    const uint32_t buf = stg + (uint32_t)(chunk & 1) * 4096u;
-    if (tma_store) {
-      // the bulk store that last read this buffer (two chunks ago) must have finished reading it
-      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+#define EPI_MARK(slot) do { if (p.stamps != nullptr && threadIdx.x == 64) p.stamps[STAMP_STRIDE * blockIdx.x + (slot)] = clock64(); } while (0)
+  for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+    if (n0 + c0 >= n_end) break;
+    if (p.stamps != nullptr && threadIdx.x == 64 && ((c0 - c_begin) >> 5) < 8)
+      p.stamps[STAMP_STRIDE * blockIdx.x + 19 + ((c0 - c_begin) >> 5)] = clock64();   // bring-up: start of each chunk
+    const uint32_t buf = stg.buf(issued % stg.nbuf);
+    if (tma_store && issued >= stg.nbuf) {
+      // the bulk store that last read this buffer (nbuf chunks ago) must have finished reading it
+      if (lane == 0) bulk_wait_read(stg.nbuf - 1);
       __syncwarp();
     }
     EPI_STAMP(0);
     uint32_t r[32];
     tmem_ld32(taddr + c0, r);                    // lane = accumulator row, 32 consecutive columns
     EPI_STAMP(1);
-    if (n0 + c0 >= n_end) break;
+    EPI_MARK(27);
     if (recv) {
       // split-K: add the peer CTA's partial sums of this chunk (same row-per-lane, XOR-swizzled layout)
       const uint32_t rb = recv + (uint32_t)((c0 - c_begin) >> 5) * 4096u + (uint32_t)lane * 128u;
@@ -222,22 +279,17 @@ __device__ __forceinline__ void epilogue_tile(const TcParams &p, const CUtensorM
     EPI_STAMP(2);
     if (simple) {
       if (has_bias) {
-        // the 32 bias values of this chunk: one coalesced load, staged in a 128-byte per-warp slot and
-        // read back as 8 broadcast float4 (32 dependent register shuffles cost ~1000 cycles per chunk)
-        const int nb = n0 + c0 + lane;
-        const float bl = (nb < n_end) ? __ldg(bias + nb) : 0.0f;
-        asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_slot + (uint32_t)lane * 4u), "f"(bl) : "memory");
-        __syncwarp();
+        // the tile's bias slice was staged in shared memory before the accumulator was ready:
+        // 8 broadcast float4 reads per chunk, no global latency on this path
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
           float b[4];
           asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b[0]), "=f"(b[1]), "=f"(b[2]), "=f"(b[3])
-                       : "r"(bias_slot + (uint32_t)g * 16u));
+                       : "r"(bias_smem + (uint32_t)(c0 + 4 * g) * 4u));
 #pragma unroll
           for (int e = 0; e < 4; ++e)
             r[4 * g + e] = __float_as_uint(epi_value<ACT, DACT>(alpha, beta, true, false, __uint_as_float(r[4 * g + e]), b[e], 1.0f, 0.0f));
         }
-        __syncwarp();
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j)
@@ -251,16 +303,15 @@ __device__ __forceinline__ void epilogue_tile(const TcParams &p, const CUtensorM
       asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(buf + (uint32_t)lane * 128u + (uint32_t)((g ^ (lane & 7)) << 4)),
                    "r"(r[4 * g]), "r"(r[4 * g + 1]), "r"(r[4 * g + 2]), "r"(r[4 * g + 3]) : "memory");
     EPI_STAMP(3);
+    EPI_MARK(28);
     if (!simple) {
       __syncwarp();
       // row-contiguous domain: 8 lanes cover the 128 bytes of one row, global accesses coalesce
       const int n = n0 + c0 + 4 * cg;
       float bv[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-      if (has_bias) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-          if (n + e < n_end) bv[e] = __ldg(bias + n + e);
-      }
+      if (has_bias)
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(bv[0]), "=f"(bv[1]), "=f"(bv[2]), "=f"(bv[3])
+                     : "r"(bias_smem + (uint32_t)(c0 + 4 * cg) * 4u));
       const bool full4 = n + 4 <= n_end;
       // all global reads of the chunk are issued before the first use (8 independent 16-byte loads per lane)
       // (one source per epilogue kind: the derivative source for data gradients, old C for beta != 0)
@@ -311,22 +362,31 @@ __device__ __forceinline__ void epilogue_tile(const TcParams &p, const CUtensorM
       }
     }
     EPI_STAMP(4);
+    EPI_MARK(29);
     if (tma_store) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the TMA
       __syncwarp();
+      EPI_MARK(30);
       if (lane == 0) tma_store_2d(map_c, buf, n0 + c0, m_base);      // rows/columns past M/N are clipped
+      ++issued;
+      EPI_MARK(31);
     } else {
       __syncwarp();
     }
     EPI_STAMP(5);
   }
 #undef EPI_STAMP
+#undef EPI_MARK
   if (timing)
-    for (int i = 0; i < 6; ++i) p.stamps[16 * blockIdx.x + 8 + i] += tacc[i];
+    for (int i = 0; i < 6; ++i) p.stamps[STAMP_STRIDE * blockIdx.x + 8 + i] += tacc[i];
 }
 
+// 128 registers per thread: the 10 warps land 3/3/2/2 on the four SM sub-partitions, and a sub-partition
+// with three contraction warps must still have room for a warp of a light kernel (SGD, bias gradient)
+// that runs beside it; at the 168 registers a 320-thread launch bound allows nothing else became resident
+// (tools/ubench_coresident.cu)
 template <bool A_KMAJOR, bool B_KMAJOR>
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __maxnreg__(128)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_c, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -341,10 +401,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   auto tfull_bar = [&](int a) { return bars + 8 * (2 * MAX_STAGES + a); };
   auto tempty_bar = [&](int a) { return bars + 8 * (2 * MAX_STAGES + 2 + a); };
   const uint32_t tmem_slot = bars + 8 * (2 * MAX_STAGES + 4);
+  // split-K exchange: xready = "the peer's ring is idle, send", xdone = "the peer's partial sums have landed here"
+  // xack = "the peer has everything it needs from this CTA's shared memory" (the source of the bulk copies)
+  const uint32_t xready_bar = bars + 8 * (2 * MAX_STAGES + 5), xdone_bar = bars + 8 * (2 * MAX_STAGES + 6);
+  const uint32_t xack_bar = bars + 8 * (2 * MAX_STAGES + 7);
+  const uint32_t bias_smem = bars + 256u;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  long long *stamp = p.stamps ? p.stamps + 16 * blockIdx.x : nullptr;
-  if (stamp && threadIdx.x == 0) stamp[0] = clock64();
+  long long *stamp = p.stamps ? p.stamps + STAMP_STRIDE * blockIdx.x : nullptr;
+  if (stamp && threadIdx.x == 0) {
+    stamp[0] = clock64();
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    stamp[14] = (long long)gt;
+  }
   const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + p.BN - 1) / p.BN;
   const int num_tiles = tiles_m * tiles_n;
   const int num_k = (p.K + BK - 1) / BK;
@@ -355,19 +425,56 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int kb_hi = (p.splitk == 2 && crank == 0) ? kb_half : num_k;
   const int tile_first = (p.splitk == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int tile_step = (p.splitk == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  // TMA always writes (and signals) whole boxes, also when they are partly out of bounds
+  const uint32_t stage_tx = (uint32_t)A_BYTES + (B_KMAJOR ? (uint32_t)p.BN * BK * 4 : (uint32_t)((p.BN + 31) / 32) * 4096u);
 
+  // one TMA per operand per stage.  MN-major operands are described as 3-D tensors
+  // {32 contiguous elements, K rows, MN/32 chunks}: a box {32, 32, tile/32} lands as consecutive
+  // 4 KiB [32 k][32 mn] blocks, the layout the MN-major UMMA descriptor walks (LBO = 4 KiB).
+  // (issuing the 4 + 8 separate 4 KiB boxes of a 128x256 tile cost ~100 cycles each and made the
+  // weight-gradient main loop TMA-issue bound: 1150 instead of 610 cycles per k-block)
+  auto load_stage = [&](int stage, int m0, int n0, int kb) {
+    const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_BYTES;
+    mbar_expect_tx(full_bar(stage), stage_tx);
+    const int k0 = kb * BK;
+    if (A_KMAJOR) tma_load_2d(sa, &map_a, full_bar(stage), k0, m0);            // box {32 k, 128 rows}
+    else tma_load_3d(sa, &map_a, full_bar(stage), 0, k0, m0 >> 5);             // box {32 m, 32 k, 4}
+    if (B_KMAJOR) tma_load_2d(sb, &map_b, full_bar(stage), k0, n0);            // box {32 k, BN rows}
+    else tma_load_3d(sb, &map_b, full_bar(stage), 0, k0, n0 >> 5);             // box {32 n, 32 k, BN/32}
+  };
+
+  // the first pass over the ring needs no empty-slot wait: thread 0 initialises the barriers and starts
+  // the first loads right away, so that their latency overlaps the TMEM allocation and the CTA-wide sync
+  int pre_issued = 0;
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 32 * EPI_WARPS); }
+    mbar_init(xready_bar, 1);
+    mbar_init(xdone_bar, 1);
+    mbar_init(xack_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (p.splitk == 2) {
+      // the peer ships 4 quadrants x (chunks this CTA owns) x 4 KiB of partial sums
+      const int nch = (p.BN + 31) >> 5, own0 = (nch + 1) >> 1;
+      mbar_expect_tx(xdone_bar, (uint32_t)(4 * (crank ? nch - own0 : own0)) * 4096u);
+    }
+    if (tile_first < num_tiles) {
+      const int m0 = (tile_first / tiles_n) * BM, n0 = (tile_first % tiles_n) * p.BN;
+      const int npre = min(STAGES, kb_hi - kb_lo);
+      for (; pre_issued < npre; ++pre_issued) load_stage(pre_issued, m0, n0, kb_lo + pre_issued);
+    }
+    if (stamp) stamp[2] = clock64();
     if (p.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c) : "memory");
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  // split-K pair: nobody touches the peer's barriers before the peer has initialised them.  The arrive is
+  // here, the matching wait sits right before the first remote access (epilogue warps) or at the end of
+  // the role (producer / MMA warps), so the handshake costs nothing.
+  if (p.splitk == 2) cluster_arrive_relaxed();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   if (stamp && threadIdx.x == 0) stamp[1] = clock64();
@@ -375,28 +482,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (warp == 0) {
     // ================================ TMA producer ================================
     if (lane == 0) {
-      // TMA always writes (and signals) whole boxes, also when they are partly out of bounds
-      const uint32_t stage_tx = (uint32_t)A_BYTES + (B_KMAJOR ? (uint32_t)p.BN * BK * 4 : (uint32_t)((p.BN + 31) / 32) * 4096u);
-      (void)staging;
       int stage = 0;
       uint32_t phase = 0;
+      int skip = pre_issued;   // k-blocks of the first tile already in flight
       for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
         const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * p.BN;
         for (int kb = kb_lo; kb < kb_hi; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1);
-          const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_BYTES;
-          mbar_expect_tx(full_bar(stage), stage_tx);
-          const int k0 = kb * BK;
-          // one TMA per operand per stage.  MN-major operands are described as 3-D tensors
-          // {32 contiguous elements, K rows, MN/32 chunks}: a box {32, 32, tile/32} lands as consecutive
-          // 4 KiB [32 k][32 mn] blocks, the layout the MN-major UMMA descriptor walks (LBO = 4 KiB).
-          // (issuing the 4 + 8 separate 4 KiB boxes of a 128x256 tile cost ~100 cycles each and made the
-          // weight-gradient main loop TMA-issue bound: 1150 instead of 610 cycles per k-block)
-          if (A_KMAJOR) tma_load_2d(sa, &map_a, full_bar(stage), k0, m0);            // box {32 k, 128 rows}
-          else tma_load_3d(sa, &map_a, full_bar(stage), 0, k0, m0 >> 5);             // box {32 m, 32 k, 4}
-          if (B_KMAJOR) tma_load_2d(sb, &map_b, full_bar(stage), k0, n0);            // box {32 k, BN rows}
-          else tma_load_3d(sb, &map_b, full_bar(stage), 0, k0, n0 >> 5);             // box {32 n, 32 k, BN/32}
-          if (stamp && kb == kb_lo && tile == tile_first) stamp[2] = clock64();
+          if (skip > 0) {
+            --skip;
+          } else {
+            mbar_wait(empty_bar(stage), phase ^ 1);
+            load_stage(stage, m0, n0, kb);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -434,84 +531,149 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   } else {
     // ================================ epilogue warps ==============================
     const int quad = warp & 3;                        // TMEM lanes [32*quad, 32*quad+32)
+    const int half = (warp - 2) >> 2;                 // which half of the tile's column chunks
+    const int ew = warp - 2;
+    const int et = threadIdx.x - 64;                  // 0 .. 32*EPI_WARPS-1
     int local = 0;
-    int chunk = 0;
+    int issued = 0;
     for (int tile = tile_first; tile < num_tiles; tile += tile_step, ++local) {
       const int acc = local & 1;
       const uint32_t acc_phase = (uint32_t)(local >> 1) & 1;
       const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * p.BN;
+      // the tile's bias slice -> shared memory while the contraction is still running
+      if (p.ep.bias != nullptr) {
+        epi_bar_sync();                               // every warp is done with the previous tile's slice
+        for (int j = et; j < p.BN; j += 32 * EPI_WARPS) {
+          const float bvv = (n0 + j < p.N) ? __ldg(p.ep.bias + n0 + j) : 0.0f;
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_smem + (uint32_t)j * 4u), "f"(bvv) : "memory");
+        }
+        epi_bar_sync();
+      }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       if (stamp && threadIdx.x == 64) stamp[5] = clock64();
-      int c_begin = 0, c_end = p.BN;
+      // column chunks (32 wide) of the tile this warp finishes: [c_begin, c_end)
+      const int nch = (p.BN + 31) >> 5;
+      int ch_lo = 0, ch_hi = nch;
       uint32_t recv = 0;
+      uint32_t ring_free = smem_base;                 // ring bytes from here on are free for staging (if any)
       if (p.splitk == 2) {
-        // Exchange: this CTA finishes columns [c_begin, c_end) of the tile and ships its partial sums of
-        // the other half to the peer.  The receive area is the (now idle) operand ring of the peer,
+        // Exchange: this CTA finishes the chunks [ch_lo, ch_hi) of the tile and ships its partial sums of
+        // the others to the peer.  The receive area is the (now idle) operand ring of the peer,
         // which is only safe to overwrite once the peer's MMAs have retired: cluster barrier #1.
-        const int half = ((p.BN >> 5) + 1) >> 1 << 5;         // columns owned by rank 0 (multiple of 32)
-        c_begin = crank ? half : 0;
-        c_end = crank ? p.BN : half;
-        const int s_begin = crank ? 0 : half, s_end = crank ? half : p.BN;
-        const int peer_chunks = (s_end - s_begin) >> 5, own_chunks = (c_end - c_begin + 31) >> 5;
+        const int own0 = (nch + 1) >> 1;                          // chunks owned by rank 0
+        ch_lo = crank ? own0 : 0;
+        ch_hi = crank ? nch : own0;
+        const int s_lo = crank ? 0 : own0, s_hi = crank ? own0 : nch;
+        const int peer_chunks = s_hi - s_lo, own_chunks = ch_hi - ch_lo;
         __syncwarp();
-        cluster_arrive();
-        cluster_wait();
+        cluster_wait();                                // the peer's barriers exist (arrive: after the setup sync)
+        // this CTA's accumulator is complete, so its ring is idle: tell the peer it may send
+        if (ew == 0 && lane == 0) mbar_arrive_remote(mapa_shared(xready_bar, crank ^ 1u));
+        // Stage this warp's share of the peer's chunks in the local ring (behind the receive area), in the
+        // row-per-lane XOR-swizzled layout the receiver reads; then one bulk copy per 4 KiB chunk moves it
+        // into the peer's receive area.  (Per-lane st.shared::cluster of 16-byte pieces moved < 10 B/cycle.)
         const uint32_t taddr_s = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * MAX_BN;
-        const uint32_t remote = mapa_shared(smem_base + (uint32_t)(quad * peer_chunks) * 4096u, crank ^ 1u);
-        for (int c0 = s_begin; c0 < s_end; c0 += 32) {
-          if (n0 + c0 >= p.N) break;
+        const int max_send = (peer_chunks + 1) >> 1;
+        const int my_lo = s_lo + (half ? max_send : 0), my_hi = half ? s_hi : s_lo + max_send;
+        const uint32_t send_base = smem_base + (uint32_t)(4 * own_chunks + ew * max_send) * 4096u;
+        int ns = 0;
+        for (int ch = my_lo; ch < my_hi; ++ch, ++ns) {
           uint32_t r[32];
-          tmem_ld32(taddr_s + c0, r);
-          const uint32_t dst = remote + (uint32_t)((c0 - s_begin) >> 5) * 4096u + (uint32_t)lane * 128u;
+          tmem_ld32(taddr_s + ch * 32, r);
+          const uint32_t dst = send_base + (uint32_t)ns * 4096u + (uint32_t)lane * 128u;
 #pragma unroll
           for (int g = 0; g < 8; ++g)
-            asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (uint32_t)((g ^ (lane & 7)) << 4)),
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (uint32_t)((g ^ (lane & 7)) << 4)),
                          "r"(r[4 * g]), "r"(r[4 * g + 1]), "r"(r[4 * g + 2]), "r"(r[4 * g + 3]) : "memory");
         }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
-        cluster_arrive();       // release: the stores above are visible to the peer after its wait
-        cluster_wait();
+        mbar_wait_cluster(xready_bar, 0);              // the peer's ring is idle
+        if (stamp && threadIdx.x == 64) stamp[16] = clock64();
+        if (lane == 0) {
+          const uint32_t remote = mapa_shared(smem_base + (uint32_t)(quad * peer_chunks) * 4096u, crank ^ 1u);
+          const uint32_t remote_bar = mapa_shared(xdone_bar, crank ^ 1u);
+          for (int i = 0; i < ns; ++i)
+            dsm_bulk_copy(remote + (uint32_t)(my_lo + i - s_lo) * 4096u, send_base + (uint32_t)i * 4096u, 4096u, remote_bar);
+        }
+        if (stamp && threadIdx.x == 64) stamp[17] = clock64();
+        mbar_wait_cluster(xdone_bar, 0);               // the peer's partial sums of this CTA's chunks have landed
+        if (stamp && threadIdx.x == 64) stamp[18] = clock64();
+        if (ew == 0 && lane == 0) mbar_arrive_remote(mapa_shared(xack_bar, crank ^ 1u));
         recv = smem_base + (uint32_t)(quad * own_chunks) * 4096u;
+        ring_free = smem_base + (uint32_t)(4 * own_chunks + EPI_WARPS * max_send) * 4096u;
       }
+      Staging stg;
+      int w_lo, w_hi;
+      if (tile + tile_step >= num_tiles) {
+        // last tile of this CTA: the producer has nothing more to load, the ring behind ring_free is idle.
+        // The two warps of a quadrant split the chunks; each warp gets up to 4 staging tiles of its own.
+        const int ch_mid = ch_lo + ((ch_hi - ch_lo + 1) >> 1);
+        w_lo = half ? ch_mid : ch_lo;
+        w_hi = half ? ch_hi : ch_mid;
+        const uint32_t ring_end = smem_base + (uint32_t)STAGES * STAGE_BYTES;
+        const int avail = (int)((ring_end - ring_free) / (uint32_t)(EPI_WARPS * 4096));
+        stg.base = ring_free + (uint32_t)ew * 4096u;
+        stg.stride = (uint32_t)(EPI_WARPS * 4096);
+        stg.nbuf = min(4, avail);
+        if (avail < 1) {   // cannot happen with the rings gemm_tc() sizes; stay correct anyway
+          w_lo = half ? ch_hi : ch_lo;
+          w_hi = ch_hi;
+          stg.base = staging + (uint32_t)quad * 4096u;
+          stg.nbuf = 1;
+        }
+      } else {
+        // the ring is busy with the next tile: one warp per quadrant, dedicated buffer
+        w_lo = half ? ch_hi : ch_lo;
+        w_hi = ch_hi;
+        stg.base = staging + (uint32_t)quad * 4096u;
+        stg.stride = 0;
+        stg.nbuf = 1;
+      }
+      if (recv) recv += (uint32_t)(w_lo - ch_lo) * 4096u;
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * MAX_BN;
-      const uint32_t stg = staging + (uint32_t)(warp - 2) * 8192u;
-      const uint32_t bias_slot = bars + 256u + (uint32_t)(warp - 2) * 128u;
+      const int c_begin = w_lo * 32, c_end = min(w_hi * 32, p.BN);
       // the activation / derivative kind is a compile-time constant inside each instantiation: a run-time
       // switch per element made the unrolled epilogue ~4500 instructions per 32-column chunk
+#define EPI_CALL(A, D) epilogue_tile<A, D>(p, &map_c, taddr, stg, m0 + quad * 32, n0, lane, issued, c_begin, c_end, recv, bias_smem)
       if (p.ep.dact != B200_ACT_NONE) {
         switch (p.ep.dact) {
-          case B200_ACT_LOGISTIC: epilogue_tile<B200_ACT_NONE, B200_ACT_LOGISTIC>(p, &map_c, taddr, stg, m0 + quad * 32, n0, lane, chunk, c_begin, c_end, recv, bias_slot); break;
-          case B200_ACT_TANH: epilogue_tile<B200_ACT_NONE, B200_ACT_TANH>(p, &map_c, taddr, stg, m0 + quad * 32, n0, lane, chunk, c_begin, c_end, recv, bias_slot); break;
-          default: epilogue_tile<B200_ACT_NONE, B200_ACT_RELU>(p, &map_c, taddr, stg, m0 + quad * 32, n0, lane, chunk, c_begin, c_end, recv, bias_slot); break;
+          case B200_ACT_LOGISTIC: EPI_CALL(B200_ACT_NONE, B200_ACT_LOGISTIC); break;
+          case B200_ACT_TANH: EPI_CALL(B200_ACT_NONE, B200_ACT_TANH); break;
+          default: EPI_CALL(B200_ACT_NONE, B200_ACT_RELU); break;
         }
       } else {
         switch (p.ep.act) {
-          case B200_ACT_LOGISTIC: epilogue_tile<B200_ACT_LOGISTIC, B200_ACT_NONE>(p, &map_c, taddr, stg, m0 + quad * 32, n0, lane, chunk, c_begin, c_end, recv, bias_slot); break;
-          case B200_ACT_TANH: epilogue_tile<B200_ACT_TANH, B200_ACT_NONE>(p, &map_c, taddr, stg, m0 + quad * 32, n0, lane, chunk, c_begin, c_end, recv, bias_slot); break;
-          case B200_ACT_RELU: epilogue_tile<B200_ACT_RELU, B200_ACT_NONE>(p, &map_c, taddr, stg, m0 + quad * 32, n0, lane, chunk, c_begin, c_end, recv, bias_slot); break;
-          default: epilogue_tile<B200_ACT_NONE, B200_ACT_NONE>(p, &map_c, taddr, stg, m0 + quad * 32, n0, lane, chunk, c_begin, c_end, recv, bias_slot); break;
+          case B200_ACT_LOGISTIC: EPI_CALL(B200_ACT_LOGISTIC, B200_ACT_NONE); break;
+          case B200_ACT_TANH: EPI_CALL(B200_ACT_TANH, B200_ACT_NONE); break;
+          case B200_ACT_RELU: EPI_CALL(B200_ACT_RELU, B200_ACT_NONE); break;
+          default: EPI_CALL(B200_ACT_NONE, B200_ACT_NONE); break;
         }
       }
+#undef EPI_CALL
       tc_fence_before();
       mbar_arrive(tempty_bar(acc));
       if (stamp && threadIdx.x == 64) stamp[6] = clock64();
     }
     if (p.tma_store && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    // the bulk copies of the exchange read this CTA's shared memory: stay until the peer has acknowledged
+    if (p.splitk == 2 && ew == 0) mbar_wait_cluster(xack_bar, 0);
   }
   if (warp < 2 && p.splitk == 2) {
-    // producer / MMA warps only take part in the two cluster barriers of the exchange
     __syncwarp();
-    cluster_arrive();
-    cluster_wait();
-    cluster_arrive();
-    cluster_wait();
+    cluster_wait();   // pairs with the arrive after the setup sync
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
-  if (stamp && threadIdx.x == 0) stamp[7] = clock64();
+  if (stamp && threadIdx.x == 0) {
+    stamp[7] = clock64();
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    stamp[15] = (long long)gt;
+  }
 }
 
 // ------------------------------------------------------------------ host side
@@ -720,16 +882,19 @@ int gemm_tc(b200_ctx *ctx, int transA, int transB, int M, int N, int K, const fl
   const bool a_k = (transA == 0);   // op(A)[m,k] = A[m*lda + k]
   const bool b_k = (transB != 0);   // op(B)[k,n] = B[n*ldb + k]
 
+  // SMs this launch plans for: the whole device, or the budget set while two contractions of a step are
+  // meant to run side by side (b200_set_sm_budget)
+  const int sms = ctx->sm_budget > 0 ? ctx->sm_budget : ctx->sm_count;
   TcParams p;
   p.M = M; p.N = N; p.K = K;
-  pick_tile(M, N, K, ctx->sm_count, !(s->dbg_flags & 16), &p.BN, &p.splitk);
+  pick_tile(M, N, K, sms, !(s->dbg_flags & 16), &p.BN, &p.splitk);
   if (s->force_bn) {
     p.BN = s->force_bn & 0xfff;
     p.splitk = (s->force_bn & 0x1000) ? 2 : 1;
   }
   // the ring is as deep as shared memory allows: loads are latency/bandwidth bound, so bytes in flight matter
   p.stage_bytes = (uint32_t)A_BYTES + (b_k ? (uint32_t)p.BN * BK * 4 : (uint32_t)((p.BN + 31) / 32) * 4096u);
-  p.stages = (SMEM_MAX - SMEM_EXTRA) / (int)p.stage_bytes;
+  p.stages = (SMEM_BUDGET - SMEM_EXTRA) / (int)p.stage_bytes;
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
   if (s->force_stages > 0 && s->force_stages < p.stages) p.stages = s->force_stages;
   p.ldc = ldc;
@@ -771,10 +936,16 @@ int gemm_tc(b200_ctx *ctx, int transA, int transB, int M, int N, int K, const fl
   }
 
   const int tiles = ((M + BM - 1) / BM) * tiles_n;
-  if (p.splitk == 2 && (2 * tiles > ctx->sm_count || (p.BN & 31) != 0 || (K + BK - 1) / BK < 2)) p.splitk = 1;
+  if (p.splitk == 2 && (2 * tiles > sms || (p.BN & 31) != 0 || (K + BK - 1) / BK < 2)) p.splitk = 1;
   // the exchange area of a split-K pair (half a tile per CTA) lives in the operand ring
-  if (p.splitk == 2 && (size_t)p.stages * p.stage_bytes < (size_t)(p.BN / 2 + 32) * 512u) p.splitk = 1;
-  const int grid = p.splitk == 2 ? 2 * tiles : (tiles < ctx->sm_count ? tiles : ctx->sm_count);
+  if (p.splitk == 2) {
+    // receive area (4 quadrants x own chunks) + send staging (8 warps x half of the peer's chunks), 4 KiB each
+    const int nch = (p.BN + 31) / 32, own0 = (nch + 1) / 2, own1 = nch - own0;
+    const size_t need0 = (size_t)(4 * own0 + EPI_WARPS * ((own1 + 1) / 2)) * 4096u;
+    const size_t need1 = (size_t)(4 * own1 + EPI_WARPS * ((own0 + 1) / 2)) * 4096u;
+    if ((size_t)p.stages * p.stage_bytes < (need0 > need1 ? need0 : need1)) p.splitk = 1;
+  }
+  const int grid = p.splitk == 2 ? 2 * tiles : (tiles < sms ? tiles : sms);
   if (a_k && b_k) return launch<true, true>(ctx, s, 0, ma, mb, mc, p, grid);
   if (a_k && !b_k) return launch<true, false>(ctx, s, 1, ma, mb, mc, p, grid);
   if (!a_k && b_k) return launch<false, true>(ctx, s, 2, ma, mb, mc, p, grid);

@@ -243,11 +243,27 @@ class StackANNComponent : public ANNComponent {
   // set by the trainer: stop before a trailing row-wise activation so that the loss kernel
   // can fuse log_softmax + loss + gradient
   bool defer_last_actf = false;
+  // with defer_last_actf: also stop before a trailing dot_product [+ bias] with at most 16 outputs, so that
+  // the trainer can run the whole output layer (forward, log_softmax, loss, gradient, data gradient of the
+  // layer below) as one launch; doForward then returns that layer's input and fills deferred_dot / _bias
+  bool defer_output_layer = false;
+  DotProductANNComponent *deferred_dot = nullptr;
+  BiasANNComponent *deferred_bias = nullptr;
+  // set by the trainer after that launch: the data gradient of deferred_dot already exists
+  DotProductANNComponent *precomputed_for = nullptr;
+  MatrixPtr precomputed_dx;
   // trainer: compute every component's weight gradients inside doBackprop, as soon as its error
   // input exists (reverse layer order), so that finished gradients can be all-reduced while the
   // rest of the backward pass runs.  on_gradients_ready(component) fires after each one.
   MatrixDict *interleave_grads = nullptr;
   std::function<void(ANNComponent *)> on_gradients_ready;
+  // trainer, single replica: weight gradients are issued on side branches of the step (branch 1: bias
+  // gradients and other light work, branch 2: the big contractions) while the data gradients stay on
+  // the main stream; on_backprop_issued(component) fires once the component's own data gradient has
+  // been issued, i.e. when nothing later in the step reads its weights any more.
+  bool use_branches = false;
+  bool concurrent_contractions = true;   // dgrad and wgrad of a layer side by side, half the SMs each
+  std::function<void(ANNComponent *, int branch)> on_backprop_issued;
   void prepareGradScales();   // sets grad_scale of every weight-bearing component from grad_bunch
   const std::vector<ANNComponent *> &flatComponents() const { return flat; }
  private:
@@ -341,6 +357,8 @@ class SupervisedTrainer {
   bool smooth_gradients = true;
   bool keep_gradients = false;    // write the regularised gradient back (observable grads; +4 B/param)
   bool use_cuda_graph = true;
+  bool use_branches = true;       // single replica: weight gradients / updates / statistics on side branches
+  bool fuse_output_layer = true;  // <=16-class output layer + log_softmax + MCCE + data gradient in one launch
   MatrixDict weights_table, grads, updates;
   std::vector<std::string> weights_order;   // sorted names (initialisation / API order)
   std::vector<std::string> arena_order;     // layout of the flat arenas: reverse layer order
@@ -352,6 +370,8 @@ class SupervisedTrainer {
 
  private:
   void runStep(const MatrixPtr &x, const MatrixPtr &t, int global_bunch);
+  MatrixPtr outputLayerFused(const MatrixPtr &h, const MatrixPtr &t, bool training, MatrixPtr &logp, MatrixPtr &rows,
+                             MatrixPtr &grad);
   void uploadSgdTable();
   size_t total_params = 0;
   b200_sgd_tensor *sgd_dev = nullptr;
@@ -360,8 +380,14 @@ class SupervisedTrainer {
   std::string sgd_signature;
   // staging + device-resident dataset
   MatrixPtr stage_x, stage_t;
+  // pipelined host feeding (stage / stepStaged): two staging slots filled on a copy stream, so that the
+  // host-to-device copy of bunch k+1 runs while bunch k is being trained
+  MatrixPtr pipe_x[2], pipe_t[2];
+  void *copy_stream = nullptr, *ev_copied[2] = {nullptr, nullptr}, *ev_trained[2] = {nullptr, nullptr};
+  bool slot_trained[2] = {false, false};
+  int next_slot = 0, staged_slot = -1;
   struct Graph;
-  std::map<int, Graph *> graphs;   // bunch size -> captured step
+  std::map<std::pair<int, const float *>, Graph *> graphs;   // (bunch size, input buffer) -> captured step
 };
 
 bool luaPatternMatch(const std::string &pattern, const std::string &s);

@@ -3,6 +3,7 @@
 // recognised runs into single launches.
 #include <math.h>
 
+#include <exception>
 #include <sstream>
 
 #include "ann.h"
@@ -408,9 +409,25 @@ MatrixPtr StackANNComponent::doForward(const MatrixPtr &in, bool during_training
   input = in;
   MatrixPtr cur = in;
   size_t n = flat.size();
+  deferred_dot = nullptr;
+  deferred_bias = nullptr;
   if (defer_last_actf) {
     auto *la = dynamic_cast<ActivationFunctionANNComponent *>(flat.back());
-    if (la && !la->elementwise()) --n;  // the trainer runs it fused with the loss
+    if (la && !la->elementwise()) {
+      --n;  // the trainer runs it fused with the loss
+      if (defer_output_layer && fuse && n >= 1) {
+        size_t j = n;
+        auto *b = dynamic_cast<BiasANNComponent *>(flat[j - 1]);
+        if (b && j >= 2) --j;
+        auto *d = dynamic_cast<DotProductANNComponent *>(flat[j - 1]);
+        if (d && d->weights_matrix && d->getOutputSize() >= 3 && d->getOutputSize() <= 16 &&
+            d->getInputSize() % 4 == 0 && (!b || b->bias_vector)) {
+          deferred_dot = d;
+          deferred_bias = (j < n) ? b : nullptr;
+          n = j - 1;
+        }
+      }
+    }
   }
   size_t i = 0;
   while (i < n) {
@@ -475,12 +492,36 @@ MatrixPtr StackANNComponent::doBackprop(const MatrixPtr &err) {
   const int n = (int)flat.size();
   while (i >= 0) {
     ANNComponent *c = flat[i];
+    int branch = -1;
+    bool had_grads = false;
     if (interleave_grads && c->hasWeightsName() && cur) {
+      had_grads = true;
       // the error input of this component is final: its weight gradients can be computed now
       c->error_input = cur;
+      if (use_branches) {
+        auto *d = dynamic_cast<DotProductANNComponent *>(c);
+        const bool heavy = (d && d->getOutputSize() > 16) || dynamic_cast<ConvolutionANNComponent *>(c);
+        branch = heavy ? 2 : 1;
+        check(b200_branch_begin(ctx, branch));
+        // a layer's weight gradient (branch) and data gradient (main stream) are independent: plan each
+        // persistent contraction for half of the SMs so that they really run side by side
+        if (d && heavy && concurrent_contractions && !(i == 0 && skip_input_gradient)) {
+          int sms = 0;
+          check(b200_sm_count(ctx, &sms));
+          check(b200_set_sm_budget(ctx, sms / 2));
+        }
+      }
       c->computeAllGradients(*interleave_grads);
       if (on_gradients_ready) on_gradients_ready(c);
+      if (use_branches) check(b200_branch_end(ctx));
     }
+    struct Issued {   // fires on every way out of this iteration
+      StackANNComponent *s; ANNComponent *c; int branch; bool had_grads;
+      ~Issued() noexcept(false) {
+        if (s->use_branches) b200_set_sm_budget(s->ctx, 0);
+        if (had_grads && s->on_backprop_issued && !std::uncaught_exceptions()) s->on_backprop_issued(c, branch);
+      }
+    } issued{this, c, branch, had_grads};
     if (fuse) {
       auto *la = dynamic_cast<ActivationFunctionANNComponent *>(c);
       if (la && i == n - 1 && last_actf_backprop_is_identity) {
@@ -501,9 +542,14 @@ MatrixPtr StackANNComponent::doBackprop(const MatrixPtr &err) {
           continue;
         }
         const int bunch = cur->rows(), K = (int)dot->getInputSize(), N = (int)dot->getOutputSize();
-        MatrixPtr dx = Matrix::create(ctx, dims2(bunch, K));
-        check(b200_linear_bwd_data(ctx, bunch, N, K, cur->data, N, dot->weights_matrix->data, K,
-                                   pa ? pa->act : B200_ACT_NONE, pa ? pa->output->data : nullptr, K, dx->data, K));
+        MatrixPtr dx;
+        if (dot == precomputed_for && precomputed_dx) {
+          dx = precomputed_dx;   // produced by the fused output-layer launch (same pa decision)
+        } else {
+          dx = Matrix::create(ctx, dims2(bunch, K));
+          check(b200_linear_bwd_data(ctx, bunch, N, K, cur->data, N, dot->weights_matrix->data, K,
+                                     pa ? pa->act : B200_ACT_NONE, pa ? pa->output->data : nullptr, K, dx->data, K));
+        }
         dot->error_output = pa ? MatrixPtr() : dx;
         if (pa) {
           // dx already holds d(loss)/d(pre-activation) of the previous layer

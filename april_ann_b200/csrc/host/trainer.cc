@@ -142,6 +142,10 @@ SupervisedTrainer::SupervisedTrainer(b200_ctx *ctx, const std::shared_ptr<StackA
     : ctx(ctx), net(net), loss(ctx, loss_kind, 0), bunch_size(bunch_size) {
   if (!ctx) throw Error(B200_ERR_CUDA, "trainer needs a device context: this build has no CPU path");
   if (const char *e = getenv("B200_DP_BUCKET_MB")) dp_bucket_bytes = (size_t)(atof(e) * 1048576.0);
+  // tuning switches (A/B measurements): side branches of the step, and dgrad || wgrad of a layer
+  if (const char *e = getenv("B200_BRANCHES")) use_branches = atoi(e) != 0;
+  if (const char *e = getenv("B200_FUSE_OUTPUT")) fuse_output_layer = atoi(e) != 0;
+  if (const char *e = getenv("B200_CONCURRENT_BWD")) net->concurrent_contractions = atoi(e) != 0;
   void *p;
   check(b200_malloc(ctx, &p, 2 * sizeof(int64_t)));
   count_dev = (int64_t *)p;
@@ -150,6 +154,14 @@ SupervisedTrainer::SupervisedTrainer(b200_ctx *ctx, const std::shared_ptr<StackA
 SupervisedTrainer::~SupervisedTrainer() {
   b200_sync(ctx);
   for (auto &kv : graphs) delete kv.second;
+  if (copy_stream) {
+    cudaStreamSynchronize((cudaStream_t)copy_stream);
+    for (int i = 0; i < 2; ++i) {
+      cudaEventDestroy((cudaEvent_t)ev_copied[i]);
+      cudaEventDestroy((cudaEvent_t)ev_trained[i]);
+    }
+    cudaStreamDestroy((cudaStream_t)copy_stream);
+  }
   if (count_dev) b200_free(ctx, count_dev);
   if (sgd_dev) b200_free(ctx, sgd_dev);
 }
@@ -289,6 +301,43 @@ void SupervisedTrainer::uploadSgdTable() {
   }
 }
 
+// The whole output layer in one launch (b200_output_layer_fused): h = the input of net->deferred_dot.
+// Returns the logits; fills logp / loss rows / gradient and, when training, hands the data gradient of
+// the layer below to the stack (precomputed_dx) with the same fusion decision doBackprop would take.
+MatrixPtr SupervisedTrainer::outputLayerFused(const MatrixPtr &h, const MatrixPtr &t, bool training, MatrixPtr &logp,
+                                              MatrixPtr &rows, MatrixPtr &grad) {
+  DotProductANNComponent *dot = net->deferred_dot;
+  BiasANNComponent *bias = net->deferred_bias;
+  if (h->dims.size() < 2 || (unsigned)h->cols() != dot->getInputSize())
+    throw Error(B200_ERR_BAD_ARG, "Incorrect input size [" + dot->getName() + "]");
+  const int bunch = h->rows(), K = (int)dot->getInputSize(), N = (int)dot->getOutputSize();
+  if (!t || t->size() != (size_t)bunch * N) throw Error(128, "Different token sizes found: input vs target");
+  MatrixPtr logits = Matrix::create(ctx, std::vector<int>{bunch, N});
+  if (!logp) logp = Matrix::create(ctx, logits->dims);
+  rows = Matrix::create(ctx, std::vector<int>{bunch});
+  if (training) grad = Matrix::create(ctx, logits->dims);
+  // the layer below: an element-wise activation whose output is h -> its derivative is applied here
+  const auto &flat = net->flatComponents();
+  size_t idx = 0;
+  while (idx < flat.size() && flat[idx] != dot) ++idx;
+  ActivationFunctionANNComponent *pa = idx >= 1 ? dynamic_cast<ActivationFunctionANNComponent *>(flat[idx - 1]) : nullptr;
+  if (pa && (!pa->elementwise() || !pa->output)) pa = nullptr;
+  MatrixPtr dx;
+  const bool want_dx = training && !(idx == 0 && net->skip_input_gradient) && (!pa || pa->output->data == h->data);
+  if (want_dx) dx = Matrix::create(ctx, std::vector<int>{bunch, K});
+  check(b200_output_layer_fused(ctx, bunch, N, K, h->data, K, dot->weights_matrix->data, K,
+                                bias ? bias->bias_vector->data : nullptr, t->data, logits->data, logp->data, rows->data,
+                                grad ? grad->data : nullptr, pa ? pa->act : B200_ACT_NONE, dx ? dx->data : nullptr, K));
+  dot->input = h;
+  if (bias) { bias->input.reset(); bias->output.reset(); }
+  (bias ? (ANNComponent *)bias : (ANNComponent *)dot)->output = logits;
+  if (dx) {
+    net->precomputed_for = dot;
+    net->precomputed_dx = dx;
+  }
+  return logits;
+}
+
 // One training step enqueued on the stream: supervised.lua:769-819 + optimizer_sgd.lua:50-100.
 void SupervisedTrainer::runStep(const MatrixPtr &x, const MatrixPtr &t, int global_bunch) {
   net->reset();
@@ -298,12 +347,20 @@ void SupervisedTrainer::runStep(const MatrixPtr &x, const MatrixPtr &t, int glob
       net->fuse && last && last->act == B200_ACT_LOG_SOFTMAX && loss.kind == LOSS_MULTI_CLASS_CROSS_ENTROPY;
   MatrixPtr out, rows, grad;
   net->skip_input_gradient = true;
+  net->precomputed_for = nullptr;
+  net->precomputed_dx.reset();
   if (fused_loss) {
     net->defer_last_actf = true;
+    net->defer_output_layer = fuse_output_layer;
     MatrixPtr logits = net->doForward(x, true);
     net->defer_last_actf = false;
-    grad = Matrix::create(ctx, logits->dims);
-    loss.fusedLogSoftmaxMCCE(logits, t, out, rows, grad);
+    net->defer_output_layer = false;
+    if (net->deferred_dot) {
+      logits = outputLayerFused(logits, t, true, out, rows, grad);
+    } else {
+      grad = Matrix::create(ctx, logits->dims);
+      loss.fusedLogSoftmaxMCCE(logits, t, out, rows, grad);
+    }
     last->input = logits;
     last->output = out;
     net->output = out;
@@ -314,71 +371,134 @@ void SupervisedTrainer::runStep(const MatrixPtr &x, const MatrixPtr &t, int glob
     grad = loss.computeGradient(out, t);
     net->last_actf_backprop_is_identity = false;
   }
-  // backward pass with the weight gradients interleaved (reverse layer order).  With a replica
-  // group, finished gradients are all-reduced bucket by bucket on the communication stream while
-  // the rest of the backward pass runs, and each bucket is updated as soon as it has arrived.
+  // backward pass with the weight gradients interleaved (reverse layer order).
   net->grad_bunch = smooth_gradients ? (float)global_bunch : 0.0f;
   net->prepareGradScales();
   const int nt = (int)arena_order.size();
-  std::vector<char> done(nt, 0);
-  std::vector<std::pair<int, int>> buckets;   // [first, last) tensor indices in arena order
-  int next = 0;
-  auto flush = [&](bool force) {
-    int hi = next;
-    size_t bytes = 0;
-    while (hi < nt && done[hi]) { bytes += grads[arena_order[hi]]->size() * sizeof(float); ++hi; }
-    if (hi == next) return;
-    if (!force && bytes < dp_bucket_bytes && hi < nt) return;
-    if ((int)buckets.size() >= 15 && hi < nt) return;   // keep one slot for the tail
-    float *base = grads[arena_order[next]]->data;
-    const MatrixPtr &last = grads[arena_order[hi - 1]];
-    const size_t count = (size_t)(last->data - base) + last->size();
-    check(b200_allreduce_sum_async(ctx, base, count, (int)buckets.size()));
-    buckets.emplace_back(next, hi);
-    next = hi;
+  const double decay = optimizer.getOption("decay");
+  const int wb = keep_gradients ? B200_SGD_WRITE_BACK_GRAD : 0;
+  auto tensorIndex = [&](const std::string &wn) {
+    for (int i = 0; i < nt; ++i)
+      if (arena_order[i] == wn) return i;
+    return -1;
   };
-  if (dp_nranks > 1) {
-    net->on_gradients_ready = [&](ANNComponent *c) {
-      // a tensor is final once every component that shares it has contributed
-      const std::string &wn = c->getWeightsName();
-      bool pending = false, seen = false;
-      const auto &flat = net->flatComponents();
-      for (auto *o : flat) {
-        if (o == c) { seen = true; continue; }
-        if (!seen && o->hasWeightsName() && o->getWeightsName() == wn) pending = true;   // earlier layers come later
-      }
-      if (pending) return;
-      for (int i = 0; i < nt; ++i)
-        if (arena_order[i] == wn) done[i] = 1;
-      flush(false);
-    };
-  }
+  // a tensor is final once the earliest (in forward order) component that shares it has contributed
+  auto isFinalContribution = [&](ANNComponent *c) {
+    for (auto *o : net->flatComponents()) {
+      if (o == c) return true;
+      if (o->hasWeightsName() && o->getWeightsName() == c->getWeightsName()) return false;
+    }
+    return true;
+  };
   net->interleave_grads = &grads;
-  try {
-    net->doBackprop(grad);
-  } catch (...) {
+  std::vector<char> done(nt, 0);
+  auto cleanup = [&]() {
     net->interleave_grads = nullptr;
     net->on_gradients_ready = nullptr;
-    throw;
-  }
-  net->interleave_grads = nullptr;
-  net->on_gradients_ready = nullptr;
-  net->last_actf_backprop_is_identity = false;
+    net->on_backprop_issued = nullptr;
+    net->use_branches = false;
+    net->last_actf_backprop_is_identity = false;
+  };
   if (dp_nranks > 1) {
+    // Replica group: finished gradients are all-reduced bucket by bucket on the communication stream
+    // while the rest of the backward pass runs, and each bucket is updated as soon as it has arrived.
+    std::vector<std::pair<int, int>> buckets;   // [first, last) tensor indices in arena order
+    int next = 0;
+    auto flush = [&](bool force) {
+      int hi = next;
+      size_t bytes = 0;
+      while (hi < nt && done[hi]) { bytes += grads[arena_order[hi]]->size() * sizeof(float); ++hi; }
+      if (hi == next) return;
+      if (!force && bytes < dp_bucket_bytes && hi < nt) return;
+      if ((int)buckets.size() >= 15 && hi < nt) return;   // keep one slot for the tail
+      float *base = grads[arena_order[next]]->data;
+      const MatrixPtr &last = grads[arena_order[hi - 1]];
+      const size_t count = (size_t)(last->data - base) + last->size();
+      check(b200_allreduce_sum_async(ctx, base, count, (int)buckets.size()));
+      buckets.emplace_back(next, hi);
+      next = hi;
+    };
+    net->on_gradients_ready = [&](ANNComponent *c) {
+      if (!isFinalContribution(c)) return;
+      const int i = tensorIndex(c->getWeightsName());
+      if (i >= 0) done[i] = 1;
+      flush(false);
+    };
+    try {
+      net->doBackprop(grad);
+    } catch (...) {
+      cleanup();
+      throw;
+    }
+    cleanup();
     for (int i = 0; i < nt; ++i) done[i] = 1;   // tensors no component touched this step stay zero: reduce them too
     flush(true);
     for (size_t b = 0; b < buckets.size(); ++b) {
       check(b200_comm_wait(ctx, (int)b));
-      check(b200_sgd_multi_tensor(ctx, buckets[b].second - buckets[b].first, sgd_dev + buckets[b].first,
-                                  sgd_host.data() + buckets[b].first, optimizer.getOption("decay"), count_dev,
-                                  keep_gradients ? 1 : 0));
+      const int last = (b + 1 == buckets.size()) ? B200_SGD_INCREMENT_COUNT : 0;
+      check(b200_sgd_multi_tensor_ex(ctx, buckets[b].second - buckets[b].first, sgd_dev + buckets[b].first,
+                                     sgd_host.data() + buckets[b].first, decay, count_dev, wb | last));
     }
+    loss.accumLoss(rows);
   } else {
-    check(b200_sgd_multi_tensor(ctx, (int)sgd_host.size(), sgd_dev, sgd_host.data(), optimizer.getOption("decay"),
-                                count_dev, keep_gradients ? 1 : 0));
+    // Single replica: the loss statistics, the weight gradients and the update of every finished tensor
+    // run on side branches; only the data gradients stay on the critical path.  The update of a tensor
+    // is issued once its gradient is final AND the data gradient that reads the weights has been
+    // issued (on_backprop_issued).  It is held back by one tensor so that the very last one can run on
+    // the main stream after the join and bump the step counter.
+    if (use_branches) check(b200_branch_begin(ctx, 0));
+    loss.accumLoss(rows);
+    if (use_branches) check(b200_branch_end(ctx));
+    int pending = -1, pending_branch = -1;
+    auto issuePending = [&](bool last) {
+      if (pending < 0) return;
+      // updates have their own branch (0): they never sit in front of the next gradient kernel of
+      // branch 1 / 2; they wait for the branch that produced the gradient.  The last one of the step goes
+      // to the branch of its own gradient kernel instead (nothing else will be issued there), so that it
+      // does not queue behind the big update still running on branch 0.
+      if (use_branches) {
+        const int b = (last && pending_branch > 0) ? pending_branch : 0;
+        check(b200_branch_begin(ctx, b));
+        if (pending_branch > 0 && pending_branch != b) check(b200_branch_wait(ctx, pending_branch));
+      }
+      const bool bump = last && !use_branches;   // serial flow: the last update launch bumps the step counter
+      check(b200_sgd_multi_tensor_ex(ctx, 1, sgd_dev + pending, sgd_host.data() + pending, decay, count_dev,
+                                     wb | (bump ? B200_SGD_INCREMENT_COUNT : 0)));
+      if (use_branches) check(b200_branch_end(ctx));
+      done[pending] = 1;
+      pending = -1;
+    };
+    net->use_branches = use_branches;
+    net->on_backprop_issued = [&](ANNComponent *c, int branch) {
+      if (!isFinalContribution(c)) return;
+      const int i = tensorIndex(c->getWeightsName());
+      if (i < 0 || done[i] || i == pending) return;
+      issuePending(false);
+      pending = i;
+      pending_branch = branch;
+    };
+    try {
+      net->doBackprop(grad);
+      // tensors no component touched this step (zero gradient) still take their momentum / decay step
+      for (int i = 0; i < nt; ++i) {
+        if (done[i] || i == pending) continue;
+        issuePending(false);
+        pending = i;
+        pending_branch = 1;
+      }
+      const bool had_pending = pending >= 0;
+      issuePending(true);
+      check(b200_branch_join_all(ctx));
+      // with branches the updates of a step run on several streams: the counter is bumped once they have
+      // all been joined
+      if (use_branches || !had_pending) check(b200_counter_increment(ctx, count_dev));
+    } catch (...) {
+      cleanup();
+      b200_branch_join_all(ctx);
+      throw;
+    }
+    cleanup();
   }
-  check(b200_counter_increment(ctx, count_dev));
-  loss.accumLoss(rows);
   last_loss_rows = rows;
   last_output = out;
 }
@@ -394,10 +514,16 @@ void SupervisedTrainer::trainStepDevice(const MatrixPtr &x, const MatrixPtr &t) 
   cudaStream_t stream = (cudaStream_t)b200_stream(ctx);
   Graph *g = nullptr;
   if (use_cuda_graph) {
-    auto it = graphs.find(bunch);
+    const auto key = std::make_pair(bunch, (const float *)x->data);
+    auto it = graphs.find(key);
     if (it == graphs.end()) {
+      if (graphs.size() >= 16) {   // callers that feed ever-changing buffers: do not hoard graphs
+        b200_sync(ctx);
+        for (auto &kv : graphs) delete kv.second;
+        graphs.clear();
+      }
       g = new Graph();
-      graphs[bunch] = g;
+      graphs[key] = g;
     } else {
       g = it->second;
     }
@@ -454,9 +580,12 @@ void SupervisedTrainer::validateStepDevice(const MatrixPtr &x, const MatrixPtr &
   MatrixPtr out, rows, nograd;
   if (fused_loss) {
     net->defer_last_actf = true;
+    net->defer_output_layer = fuse_output_layer;
     MatrixPtr logits = net->doForward(x, false);
     net->defer_last_actf = false;
-    loss.fusedLogSoftmaxMCCE(logits, t, out, rows, nograd);
+    net->defer_output_layer = false;
+    if (net->deferred_dot) logits = outputLayerFused(logits, t, false, out, rows, nograd);
+    else loss.fusedLogSoftmaxMCCE(logits, t, out, rows, nograd);
     last->input = logits;
     last->output = out;
     net->output = out;
@@ -580,16 +709,44 @@ void SupervisedTrainer::broadcastWeights() {
 }  // namespace b200
 
 namespace b200 {
-// pipelined stepping used by train loops that keep the loss on the device
+// pipelined stepping used by train loops that keep the loss on the device: stage() copies the bunch into
+// one of two staging slots on a copy stream (it only waits for the step that last trained on that slot),
+// stepStaged() makes the compute stream wait for that copy and runs the step.  With the host running
+// ahead, the copy of bunch k+1 overlaps the training of bunch k.
 void SupervisedTrainer::stage(const float *x, const float *t, int bunch) {
   const int in = (int)net->getInputSize(), out = (int)net->getOutputSize();
   if (in <= 0 || out <= 0) throw Error(B200_ERR_NOT_BUILT, "Execute build method before call this method");
-  stageView(ctx, stage_x, bunch, in, bunch_size)->fromHost(x);
-  stageView(ctx, stage_t, bunch, out, bunch_size)->fromHost(t);
+  if (!copy_stream) {
+    cudaStream_t cs;
+    cudaCheck(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking), "cudaStreamCreate");
+    copy_stream = cs;
+    for (int i = 0; i < 2; ++i) {
+      cudaEvent_t a, b;
+      cudaCheck(cudaEventCreateWithFlags(&a, cudaEventDisableTiming), "cudaEventCreate");
+      cudaCheck(cudaEventCreateWithFlags(&b, cudaEventDisableTiming), "cudaEventCreate");
+      ev_copied[i] = a;
+      ev_trained[i] = b;
+    }
+  }
+  const int s = next_slot;
+  next_slot ^= 1;
+  cudaStream_t cs = (cudaStream_t)copy_stream;
+  MatrixPtr sx = stageView(ctx, pipe_x[s], bunch, in, bunch_size);
+  MatrixPtr st = stageView(ctx, pipe_t[s], bunch, out, bunch_size);
+  if (slot_trained[s]) cudaCheck(cudaStreamWaitEvent(cs, (cudaEvent_t)ev_trained[s], 0), "cudaStreamWaitEvent");
+  cudaCheck(cudaMemcpyAsync(sx->data, x, sizeof(float) * (size_t)bunch * in, cudaMemcpyHostToDevice, cs), "H2D");
+  cudaCheck(cudaMemcpyAsync(st->data, t, sizeof(float) * (size_t)bunch * out, cudaMemcpyHostToDevice, cs), "H2D");
+  cudaCheck(cudaEventRecord((cudaEvent_t)ev_copied[s], cs), "cudaEventRecord");
+  staged_slot = s;
 }
 void SupervisedTrainer::stepStaged(int bunch) {
   const int in = (int)net->getInputSize(), out = (int)net->getOutputSize();
-  if (!stage_x || !stage_t) throw Error(B200_ERR_BAD_ARG, "step_staged before stage");
-  trainStepDevice(stageView(ctx, stage_x, bunch, in, bunch_size), stageView(ctx, stage_t, bunch, out, bunch_size));
+  if (staged_slot < 0) throw Error(B200_ERR_BAD_ARG, "step_staged before stage");
+  const int s = staged_slot;
+  cudaStream_t stream = (cudaStream_t)b200_stream(ctx);
+  cudaCheck(cudaStreamWaitEvent(stream, (cudaEvent_t)ev_copied[s], 0), "cudaStreamWaitEvent");
+  trainStepDevice(stageView(ctx, pipe_x[s], bunch, in, bunch_size), stageView(ctx, pipe_t[s], bunch, out, bunch_size));
+  cudaCheck(cudaEventRecord((cudaEvent_t)ev_trained[s], stream), "cudaEventRecord");
+  slot_trained[s] = true;
 }
 }  // namespace b200

@@ -54,7 +54,17 @@ extern "C" int b200_create(int device, b200_ctx **out) {
   b200_ctx *ctx = new b200_ctx();
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
-  CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  // the main stream carries the critical path of a step (forward, loss, data gradients): when its kernels
+  // and a side branch's are ready together, the block scheduler serves the main stream first
+  int prio_least = 0, prio_greatest = 0;
+  CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+  CUDA_TRY(cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_greatest));
+  ctx->main_stream = ctx->stream;
+  for (int i = 0; i < b200_ctx::kBranches; ++i) {
+    CUDA_TRY(cudaStreamCreateWithPriority(&ctx->side_stream[i], cudaStreamNonBlocking, prio_least));
+    CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_fork[i], cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_side[i], cudaEventDisableTiming));
+  }
   CUDA_TRY(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
   CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_compute, cudaEventDisableTiming));
   CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_comm, cudaEventDisableTiming));
@@ -67,7 +77,7 @@ extern "C" int b200_pool_trim(b200_ctx *ctx) {
   ARG_CHECK(ctx, "ctx is NULL");
   std::lock_guard<std::mutex> lk(ctx->mu);
   CUDA_TRY(cudaSetDevice(ctx->device));
-  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->main_stream));
   for (auto &kv : ctx->free_blocks) cudaFree(kv.second);
   ctx->free_blocks.clear();
   return B200_OK;
@@ -83,11 +93,17 @@ extern "C" int b200_destroy(b200_ctx *ctx) {
   gemm_tc_destroy(ctx);
   b200_pool_trim(ctx);
   for (auto &kv : ctx->live_blocks) cudaFree(kv.first);
-  if (ctx->scratch) cudaFree(ctx->scratch);
+  for (auto &p : ctx->scratch) if (p) cudaFree(p);
+  for (auto &kv : ctx->deferred_free) cudaFree(kv.second);
+  for (int i = 0; i < b200_ctx::kBranches; ++i) {
+    cudaEventDestroy(ctx->ev_fork[i]);
+    cudaEventDestroy(ctx->ev_side[i]);
+    cudaStreamDestroy(ctx->side_stream[i]);
+  }
   cudaEventDestroy(ctx->ev_compute);
   cudaEventDestroy(ctx->ev_comm);
   for (auto &e : ctx->ev_bucket) if (e) cudaEventDestroy(e);
-  cudaStreamDestroy(ctx->stream);
+  cudaStreamDestroy(ctx->main_stream);
   cudaStreamDestroy(ctx->comm_stream);
   delete ctx;
   return B200_OK;
@@ -113,8 +129,60 @@ extern "C" void *b200_stream(b200_ctx *ctx) { return ctx ? (void *)ctx->stream :
 
 extern "C" int b200_sync(b200_ctx *ctx) {
   ARG_CHECK(ctx, "ctx is NULL");
-  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->main_stream));
+  for (int i = 0; i < b200_ctx::kBranches; ++i) CUDA_TRY(cudaStreamSynchronize(ctx->side_stream[i]));
   CUDA_TRY(cudaStreamSynchronize(ctx->comm_stream));
+  return B200_OK;
+}
+
+// ---------------------------------------------------------------- side branches
+// b200_branch_begin(i): everything issued until b200_branch_end goes to side stream i, ordered after
+// what the main stream holds at this point.  b200_branch_wait(i): the current stream waits for what
+// side stream i holds.  b200_branch_join_all: the main stream waits for every open branch.  Inside
+// a stream capture these calls become the fork / join edges of the graph.
+extern "C" int b200_branch_begin(b200_ctx *ctx, int branch) {
+  ARG_CHECK(ctx, "ctx is NULL");
+  ARG_CHECK(branch >= 0 && branch < b200_ctx::kBranches, "no such branch");
+  ARG_CHECK(ctx->cur_branch < 0, "branches do not nest");
+  CUDA_TRY(cudaEventRecord(ctx->ev_fork[branch], ctx->main_stream));
+  CUDA_TRY(cudaStreamWaitEvent(ctx->side_stream[branch], ctx->ev_fork[branch], 0));
+  ctx->side_open[branch] = true;
+  ctx->cur_branch = branch;
+  ctx->stream = ctx->side_stream[branch];
+  return B200_OK;
+}
+extern "C" int b200_branch_end(b200_ctx *ctx) {
+  ARG_CHECK(ctx, "ctx is NULL");
+  ctx->cur_branch = -1;
+  ctx->stream = ctx->main_stream;
+  return B200_OK;
+}
+extern "C" int b200_branch_wait(b200_ctx *ctx, int branch) {
+  ARG_CHECK(ctx, "ctx is NULL");
+  ARG_CHECK(branch >= 0 && branch < b200_ctx::kBranches, "no such branch");
+  if (!ctx->side_open[branch] || ctx->cur_branch == branch) return B200_OK;
+  CUDA_TRY(cudaEventRecord(ctx->ev_side[branch], ctx->side_stream[branch]));
+  CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_side[branch], 0));
+  return B200_OK;
+}
+extern "C" int b200_branch_join_all(b200_ctx *ctx) {
+  ARG_CHECK(ctx, "ctx is NULL");
+  ctx->cur_branch = -1;
+  ctx->stream = ctx->main_stream;
+  for (int i = 0; i < b200_ctx::kBranches; ++i) {
+    if (!ctx->side_open[i]) continue;
+    CUDA_TRY(cudaEventRecord(ctx->ev_side[i], ctx->side_stream[i]));
+    CUDA_TRY(cudaStreamWaitEvent(ctx->main_stream, ctx->ev_side[i], 0));
+    ctx->side_open[i] = false;
+  }
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  for (auto &kv : ctx->deferred_free) ctx->free_blocks.emplace(kv.first, kv.second);
+  ctx->deferred_free.clear();
+  return B200_OK;
+}
+extern "C" int b200_set_sm_budget(b200_ctx *ctx, int sms) {
+  ARG_CHECK(ctx, "ctx is NULL");
+  ctx->sm_budget = (sms > 0 && sms < ctx->sm_count) ? sms : 0;
   return B200_OK;
 }
 
@@ -162,25 +230,31 @@ extern "C" int b200_free(b200_ctx *ctx, void *dptr) {
   std::lock_guard<std::mutex> lk(ctx->mu);
   auto it = ctx->live_blocks.find(dptr);
   ARG_CHECK(it != ctx->live_blocks.end(), "pointer was not allocated by b200_malloc on this context");
-  ctx->free_blocks.emplace(it->second, dptr);
+  bool open = false;
+  for (bool o : ctx->side_open) open = open || o;
+  // while side branches are open a block may still be in use on another stream: recycle it at the join
+  if (open) ctx->deferred_free.emplace_back(it->second, dptr);
+  else ctx->free_blocks.emplace(it->second, dptr);
   ctx->live_blocks.erase(it);
   return B200_OK;
 }
 
 void *b200_scratch(b200_ctx *ctx, size_t bytes) {
-  if (bytes <= ctx->scratch_bytes) return ctx->scratch;
-  // growing the scratch must not race with kernels still using the old one
+  const int slot = ctx->cur_branch + 1;
+  if (bytes <= ctx->scratch_bytes[slot]) return ctx->scratch[slot];
+  // growing the scratch must not race with kernels still using the old one (never happens inside a
+  // capture: the eager warm-up steps have sized every branch's scratch)
   cudaStreamSynchronize(ctx->stream);
-  if (ctx->scratch) cudaFree(ctx->scratch);
+  if (ctx->scratch[slot]) cudaFree(ctx->scratch[slot]);
   size_t sz = round_size(bytes);
-  if (cudaMalloc(&ctx->scratch, sz) != cudaSuccess) {
-    ctx->scratch = nullptr;
-    ctx->scratch_bytes = 0;
+  if (cudaMalloc(&ctx->scratch[slot], sz) != cudaSuccess) {
+    ctx->scratch[slot] = nullptr;
+    ctx->scratch_bytes[slot] = 0;
     (void)cudaGetLastError();
     return nullptr;
   }
-  ctx->scratch_bytes = sz;
-  return ctx->scratch;
+  ctx->scratch_bytes[slot] = sz;
+  return ctx->scratch[slot];
 }
 
 extern "C" int b200_host_alloc(void **hptr, size_t bytes) {

@@ -18,12 +18,14 @@
 
 namespace {
 
-constexpr int TPB = 256;
+constexpr int TPB = 128;
+constexpr int UNROLL = 4;
 
-__global__ void __launch_bounds__(TPB) sgd_kernel(const b200_sgd_tensor *__restrict__ tensors, double decay,
-                                                  const int64_t *__restrict__ count_dev, int write_back_grad) {
+__global__ void __launch_bounds__(TPB, 8) sgd_kernel(const b200_sgd_tensor *__restrict__ tensors, double decay,
+                                                  int64_t *count_dev, int flags) {
   const b200_sgd_tensor t = tensors[blockIdx.y];
-  const int64_t count = *count_dev;
+  const int64_t count = *reinterpret_cast<volatile int64_t *>(count_dev);
+  const int write_back_grad = flags & B200_SGD_WRITE_BACK_GRAD;
   const double dec = 1.0 / (1.0 + decay * (double)count);
   const float lrd = (float)((double)t.lr * dec);
   const float mt = t.momentum, l2 = t.weight_decay;
@@ -54,18 +56,34 @@ __global__ void __launch_bounds__(TPB) sgd_kernel(const b200_sgd_tensor *__restr
     float4 *w4 = reinterpret_cast<float4 *>(t.w);
     float4 *g4 = reinterpret_cast<float4 *>(t.g);
     float4 *u4 = reinterpret_cast<float4 *>(t.u);
-    for (size_t i = tid; i < n4; i += nth) {
+    // UNROLL independent (w, g, u) triples per thread are loaded before the first use: 12 x 16 bytes in
+    // flight per thread, so that the one small CTA per SM that fits beside a contraction CTA still keeps
+    // the memory system busy
+    size_t i = tid;
+    for (; i + (UNROLL - 1) * nth < n4; i += UNROLL * nth) {
+      float4 w[UNROLL], g[UNROLL], u[UNROLL];
+#pragma unroll
+      for (int j = 0; j < UNROLL; ++j) { w[j] = w4[i + j * nth]; g[j] = g4[i + j * nth]; u[j] = u4[i + j * nth]; }
+#pragma unroll
+      for (int j = 0; j < UNROLL; ++j) {
+        upd(w[j].x, g[j].x, u[j].x); upd(w[j].y, g[j].y, u[j].y); upd(w[j].z, g[j].z, u[j].z); upd(w[j].w, g[j].w, u[j].w);
+        w4[i + j * nth] = w[j];
+        u4[i + j * nth] = u[j];
+        if (write_back_grad) g4[i + j * nth] = g[j];
+      }
+    }
+    for (; i < n4; i += nth) {
       float4 w = w4[i], g = g4[i], u = u4[i];
       upd(w.x, g.x, u.x); upd(w.y, g.y, u.y); upd(w.z, g.z, u.z); upd(w.w, g.w, u.w);
       w4[i] = w;
       u4[i] = u;
       if (write_back_grad) g4[i] = g;
     }
-    for (size_t i = (n4 << 2) + tid; i < n; i += nth) {
-      float w = t.w[i], g = t.g[i], u = t.u[i];
+    for (size_t i2 = (n4 << 2) + tid; i2 < n; i2 += nth) {
+      float w = t.w[i2], g = t.g[i2], u = t.u[i2];
       upd(w, g, u);
-      t.w[i] = w; t.u[i] = u;
-      if (write_back_grad) t.g[i] = g;
+      t.w[i2] = w; t.u[i2] = u;
+      if (write_back_grad) t.g[i2] = g;
     }
   } else {
     for (size_t i = tid; i < n; i += nth) {
@@ -73,6 +91,20 @@ __global__ void __launch_bounds__(TPB) sgd_kernel(const b200_sgd_tensor *__restr
       upd(w, g, u);
       t.w[i] = w; t.u[i] = u;
       if (write_back_grad) t.g[i] = g;
+    }
+  }
+  if (flags & B200_SGD_INCREMENT_COUNT) {
+    // last update launch of the step: the last CTA to finish bumps the step counter.  Every CTA has read
+    // `count` before taking its ticket, and no other update launch of this step is still running.
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      unsigned long long *ticket = reinterpret_cast<unsigned long long *>(count_dev + 1);
+      const unsigned long long total = (unsigned long long)gridDim.x * gridDim.y;
+      if (atomicAdd(ticket, 1ull) == total - 1) {
+        *ticket = 0ull;
+        *count_dev = count + 1;
+      }
     }
   }
 }
@@ -99,17 +131,25 @@ __global__ void __launch_bounds__(TPB) max_norm_kernel(float *__restrict__ w, in
 extern "C" int b200_sgd_multi_tensor(b200_ctx *ctx, int ntensors, const b200_sgd_tensor *tensors_dev,
                                      const b200_sgd_tensor *tensors_host, double decay,
                                      const int64_t *count_dev, int write_back_grad) {
+  return b200_sgd_multi_tensor_ex(ctx, ntensors, tensors_dev, tensors_host, decay, const_cast<int64_t *>(count_dev),
+                                  write_back_grad ? B200_SGD_WRITE_BACK_GRAD : 0);
+}
+
+extern "C" int b200_sgd_multi_tensor_ex(b200_ctx *ctx, int ntensors, const b200_sgd_tensor *tensors_dev,
+                                        const b200_sgd_tensor *tensors_host, double decay, int64_t *count_dev,
+                                        int flags) {
   ARG_CHECK(ctx && tensors_dev && tensors_host && count_dev, "NULL pointer");
   if (ntensors <= 0) return B200_OK;
   size_t max_n = 0;
   for (int i = 0; i < ntensors; ++i) max_n = tensors_host[i].n > max_n ? (size_t)tensors_host[i].n : max_n;
-  size_t blocks_x = (max_n / 4 + TPB - 1) / TPB;
+  size_t blocks_x = (max_n / 4 + (size_t)TPB * UNROLL - 1) / ((size_t)TPB * UNROLL);
   // persistent-ish: cap at 8 CTAs per SM worth of blocks over all tensors
   size_t cap = (size_t)ctx->sm_count * 8;
   if (blocks_x > cap) blocks_x = cap;
   if (blocks_x < 1) blocks_x = 1;
   dim3 grid((unsigned)blocks_x, (unsigned)ntensors);
-  sgd_kernel<<<grid, TPB, 0, ctx->stream>>>(tensors_dev, decay, count_dev, write_back_grad);
+  PREFER_MAX_SMEM_ONCE(sgd_kernel);
+  sgd_kernel<<<grid, TPB, 0, ctx->stream>>>(tensors_dev, decay, count_dev, flags);
   LAUNCH_CHECK(ctx);
   for (int i = 0; i < ntensors; ++i) {
     const b200_sgd_tensor &t = tensors_host[i];

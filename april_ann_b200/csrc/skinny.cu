@@ -86,6 +86,210 @@ __global__ void __launch_bounds__(128) skinny_fwd_kernel(int M, int N, int K, co
   }
 }
 
+// ---------------------------------------------------------------- forward, K split over the warps
+// CTA = 8 warps x R bunch rows.  Warp w takes the 128-float K chunks w, w+8, ...; a lane loads one
+// float4 of each of the R rows (coalesced 512-byte row segments) and of each W row (L1/L2 hits: W is
+// a few tens of KB shared by every CTA), so all loads of a chunk are independent and in flight
+// together -- at these sizes the kernel is one memory latency long, not bandwidth bound.  The
+// R*NT per-lane partial sums of a warp are reduced with a halving butterfly (31 shuffles per 32
+// values, lane L ends up with value L), the 8 warps meet in shared memory in fixed order.
+template <int V>
+__device__ __forceinline__ void butterfly32(float (&v)[V], int base, int lane) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < o; ++i) {
+      const float a = v[base + i], b = v[base + i + o];
+      const float keep = up ? b : a, send = up ? a : b;
+      v[base + i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+}
+
+template <int NT, int R>
+__global__ void __launch_bounds__(256) skinny_fwd_ksplit_kernel(int M, int N, int K, const float *__restrict__ X, int ldx,
+                                                                const float *__restrict__ W, int ldw,
+                                                                const float *__restrict__ bias, int act,
+                                                                float *__restrict__ Y, int ldy) {
+  constexpr int V = R * NT;
+  static_assert(V % 32 == 0, "R*NT must be a multiple of 32");
+  __shared__ float red[8][V];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int m0 = blockIdx.x * R;
+  float acc[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) acc[i] = 0.0f;
+#pragma unroll 2
+  for (int k = w * 128 + lane * 4; k < K; k += 8 * 128) {
+    float4 xv[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      xv[r] = ldg4(X + (size_t)min(m0 + r, M - 1) * ldx + k);
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+      // no branch on n < N (it would put every W load in its own basic block and serialise the L2 round
+      // trips): padding columns re-read the last row, their sums are never stored
+      const float4 wv = ldg4(W + (size_t)min(n, N - 1) * ldw + k);
+#pragma unroll
+      for (int r = 0; r < R; ++r) acc[r * NT + n] = dot4(xv[r], wv, acc[r * NT + n]);
+    }
+  }
+#pragma unroll
+  for (int g = 0; g < V / 32; ++g) {
+    butterfly32<V>(acc, g * 32, lane);
+    red[w][g * 32 + lane] = acc[g * 32];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < V; i += 256) {
+    const int r = i / NT, n = i - r * NT;
+    if (m0 + r >= M || n >= N) continue;
+    float v = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v += red[j][i];
+    if (bias) v += __ldg(bias + n);
+    Y[(size_t)(m0 + r) * ldy + n] = act_apply(act, v);
+  }
+}
+
+// ---------------------------------------------------------------- classifier output layer, one launch
+// logits = X.W^T + b (N <= 16), logp = log_softmax(logits), loss_rows = MCCE(logp, target),
+// grad = d loss / d logits, and the data gradient of the layer below,
+// dX = (grad . W) (.) act'(X)  (X is that layer's activation output) -- the three launches that sit
+// between the last hidden contraction and the first big data-gradient contraction on the critical
+// path of a step.  Same K-split structure as skinny_fwd_ksplit_kernel; a CTA owns R complete rows, so
+// the row-wise loss (same arithmetic and reduction order as row_kernel<OP_LSM_MCCE, 8, 4>,
+// activation_function_kernels.cu:289-325 + loss_kernels.cu:171-185 +
+// multiclass_cross_entropy_loss_function.cc:61-71) and the data gradient of its rows need nothing from
+// other CTAs.
+template <int NT, int R>
+__global__ void __launch_bounds__(256) output_layer_fused_kernel(int M, int N, int K, const float *__restrict__ X, int ldx,
+                                                                 const float *__restrict__ W, int ldw,
+                                                                 const float *__restrict__ bias,
+                                                                 const float *__restrict__ target, float *__restrict__ logits,
+                                                                 float *__restrict__ logp_out, float *__restrict__ loss_rows,
+                                                                 float *__restrict__ grad, int dact, float *__restrict__ dX,
+                                                                 int lddx) {
+  constexpr int V = R * NT;
+  static_assert(V % 32 == 0 && R == 8, "8 rows per CTA");
+  __shared__ float red[8][V];
+  __shared__ float sg[R][NT];          // logits, then the gradient rows
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int m0 = blockIdx.x * R;
+  {
+    float acc[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc[i] = 0.0f;
+#pragma unroll 2
+    for (int k = w * 128 + lane * 4; k < K; k += 8 * 128) {
+      float4 xv[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) xv[r] = ldg4(X + (size_t)min(m0 + r, M - 1) * ldx + k);
+#pragma unroll
+      for (int n = 0; n < NT; ++n) {
+        const float4 wv = ldg4(W + (size_t)min(n, N - 1) * ldw + k);
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r * NT + n] = dot4(xv[r], wv, acc[r * NT + n]);
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < V / 32; ++g) {
+      butterfly32<V>(acc, g * 32, lane);
+      red[w][g * 32 + lane] = acc[g * 32];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < V; i += 256) {
+    const int r = i / NT, n = i - r * NT;
+    float v = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v += red[j][i];
+    if (bias && n < N) v += __ldg(bias + n);
+    sg[r][n] = v;
+    if (logits && m0 + r < M && n < N) logits[(size_t)(m0 + r) * N + n] = v;
+  }
+  __syncthreads();
+  // log_softmax + MCCE + gradient: 8 threads per row, elements t and t+8 (N <= 16)
+  if (threadIdx.x < 8 * R) {
+    const int r = threadIdx.x >> 3, t = threadIdx.x & 7;
+    const bool active = m0 + r < M;
+    const size_t off = (size_t)min(m0 + r, M - 1) * N;
+    float va[2], vb[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int c = t + 8 * j;
+      va[j] = (c < N) ? sg[r][c] : 0.0f;
+      vb[j] = (c < N) ? __ldg(target + off + c) : 0.0f;
+    }
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+      if (t + 8 * j < N) mx = fmaxf(mx, va[j]);
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+      if (t + 8 * j < N) { va[j] -= mx; sum += expf(va[j]); }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float lse = logf(sum);
+    float loss = 0.0f;
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int c = t + 8 * j;
+      if (c < N) {
+        const float logp = va[j] - lse;
+        if (active && logp_out) logp_out[off + c] = logp;
+        const float tc = fminf(fmaxf(vb[j], NEAR_ZERO_F), 1.0f - NEAR_ZERO_F);
+        if (tc > NEAR_ZERO_F) loss += -tc * logp;
+        const float cl = fminf(fmaxf(logp, logf(NEAR_ZERO_F)), logf(1.0f - NEAR_ZERO_F));
+        const float g = expf(cl) - vb[j];
+        if (active && grad) grad[off + c] = g;
+        sg[r][c] = g;
+      }
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) loss += __shfl_xor_sync(0xffffffffu, loss, o);
+    if (active && t == 0 && loss_rows) loss_rows[m0 + r] = loss;
+  }
+  if (dX == nullptr) return;
+  __syncthreads();
+  // data gradient of the rows of this CTA: thread = the same 4 input features as in the forward loop.
+  // No branches around the loads (they would serialise the L2 round trips): rows past M are clamped,
+  // only the stores are predicated.
+#pragma unroll 1
+  for (int k = w * 128 + lane * 4; k < K; k += 8 * 128) {
+    float4 wv[NT], y[R];
+#pragma unroll
+    for (int n = 0; n < NT; ++n) wv[n] = ldg4(W + (size_t)min(n, N - 1) * ldw + k);
+    if (dact != B200_ACT_NONE) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) y[r] = ldg4(X + (size_t)min(m0 + r, M - 1) * ldx + k);
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int n = 0; n < NT; ++n) {
+        const float g = (n < N) ? sg[r][n] : 0.0f;
+        a.x = fmaf(g, wv[n].x, a.x);
+        a.y = fmaf(g, wv[n].y, a.y);
+        a.z = fmaf(g, wv[n].z, a.z);
+        a.w = fmaf(g, wv[n].w, a.w);
+      }
+      if (dact != B200_ACT_NONE) {
+        a.x *= act_deriv_from_output(dact, y[r].x);
+        a.y *= act_deriv_from_output(dact, y[r].y);
+        a.z *= act_deriv_from_output(dact, y[r].z);
+        a.w *= act_deriv_from_output(dact, y[r].w);
+      }
+      if (m0 + r < M) *reinterpret_cast<float4 *>(dX + (size_t)(m0 + r) * lddx + k) = a;
+    }
+  }
+}
+
 // ---------------------------------------------------------------- forward, lane = row
 // CTA = 32 bunch rows x 16 warps; W is staged once per CTA in shared memory as [K/4][NT] float4 so
 // that every read is a warp-wide broadcast; each warp owns 1/16 of K and each lane one row, so X is
@@ -170,9 +374,23 @@ __global__ void __launch_bounds__(128) skinny_bwd_data_kernel(int M, int N, int 
       w[n][0] = (n < N) ? __ldg(W + (size_t)n * ldw + k) : 0.0f;
     }
   }
-  const int rows = min(ROWS, M - m0);
-#pragma unroll 4
-  for (int r = 0; r < rows; ++r) {
+  // all derivative-source loads of the chunk are issued before the first use (ROWS independent loads)
+  float yv[ROWS][VW];
+  if (dact != B200_ACT_NONE) {
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      const size_t m = (size_t)min(m0 + r, M - 1);
+      if (VEC) {
+        const float4 y = ldg4(Yprev + m * ldyp + k);
+        yv[r][0] = y.x; yv[r][VW > 1 ? 1 : 0] = y.y; yv[r][VW > 2 ? 2 : 0] = y.z; yv[r][VW > 3 ? 3 : 0] = y.w;
+      } else {
+        yv[r][0] = __ldg(Yprev + m * ldyp + k);
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) {
+    if (m0 + r >= M) break;
     float a[VW];
 #pragma unroll
     for (int e = 0; e < VW; ++e) a[e] = 0.0f;
@@ -184,15 +402,8 @@ __global__ void __launch_bounds__(128) skinny_bwd_data_kernel(int M, int N, int 
     }
     const size_t m = (size_t)(m0 + r);
     if (dact != B200_ACT_NONE) {
-      if (VEC) {
-        const float4 y = ldg4(Yprev + m * ldyp + k);
-        a[0] *= act_deriv_from_output(dact, y.x);
-        a[VW > 1 ? 1 : 0] *= act_deriv_from_output(dact, y.y);
-        a[VW > 2 ? 2 : 0] *= act_deriv_from_output(dact, y.z);
-        a[VW > 3 ? 3 : 0] *= act_deriv_from_output(dact, y.w);
-      } else {
-        a[0] *= act_deriv_from_output(dact, __ldg(Yprev + m * ldyp + k));
-      }
+#pragma unroll
+      for (int e = 0; e < VW; ++e) a[e] *= act_deriv_from_output(dact, yv[r][e]);
     }
     if (VEC) *reinterpret_cast<float4 *>(dX + m * lddx + k) = make_float4(a[0], a[VW > 1 ? 1 : 0], a[VW > 2 ? 2 : 0], a[VW > 3 ? 3 : 0]);
     else dX[m * lddx + k] = a[0];
@@ -381,6 +592,13 @@ bool skinny_applicable(int M, int N, int K) { return N >= 1 && N <= SK_MAXN && M
 int skinny_fwd(b200_ctx *ctx, int M, int N, int K, const float *X, int ldx, const float *W, int ldw, const float *bias,
                int act, float *Y, int ldy) {
   const bool vec = (K % 4 == 0) && (ldx % 4 == 0) && (ldw % 4 == 0) && al16(X) && al16(W);
+  if (vec && K >= 512) {
+    constexpr int R = 8;
+    const int grid = (M + R - 1) / R;
+    NT_DISPATCH(N, { skinny_fwd_ksplit_kernel<NT, R><<<grid, 256, 0, ctx->stream>>>(M, N, K, X, ldx, W, ldw, bias, act, Y, ldy); });
+    LAUNCH_CHECK(ctx);
+    return B200_OK;
+  }
   if (vec) {
     // W resident in shared memory: [K/4][NT] float4 + the 16x32xNT partials
     const int nt = pad4(N);
@@ -407,11 +625,32 @@ int skinny_fwd(b200_ctx *ctx, int M, int N, int K, const float *X, int ldx, cons
   return B200_OK;
 }
 
+extern "C" int b200_output_layer_fused(b200_ctx *ctx, int M, int N, int K, const float *X, int ldx, const float *W, int ldw,
+                                       const float *bias, const float *target, float *logits, float *logp,
+                                       float *loss_rows, float *grad, int dact, float *dX, int lddx) {
+  ARG_CHECK(ctx && X && W && target, "NULL pointer");
+  ARG_CHECK(M >= 1 && N >= 3 && K >= 1, "bad sizes");
+  const bool ok = N <= SK_MAXN && (K % 4 == 0) && (ldx % 4 == 0) && (ldw % 4 == 0) && al16(X) && al16(W) &&
+                  (dX == nullptr || ((lddx % 4 == 0) && al16(dX)));
+  if (!ok) {
+    b200_set_error("b200_output_layer_fused: needs N <= %d, K %% 4 == 0 and 16-byte aligned rows", SK_MAXN);
+    return B200_ERR_UNSUPPORTED;
+  }
+  constexpr int R = 8;
+  const int grid = (M + R - 1) / R;
+  NT_DISPATCH(N, {
+    output_layer_fused_kernel<NT, R><<<grid, 256, 0, ctx->stream>>>(M, N, K, X, ldx, W, ldw, bias, target, logits, logp,
+                                                                  loss_rows, grad, dact, dX, lddx);
+  });
+  LAUNCH_CHECK(ctx);
+  return B200_OK;
+}
+
 int skinny_bwd_data(b200_ctx *ctx, int M, int N, int K, const float *dY, int lddy, const float *W, int ldw, int dact,
                     const float *Yprev, int ldyp, float *dX, int lddx) {
   const bool vec = (K % 4 == 0) && (ldw % 4 == 0) && (lddx % 4 == 0) && al16(W) && al16(dX) &&
                    (dact == B200_ACT_NONE || ((ldyp % 4 == 0) && al16(Yprev)));
-  constexpr int ROWS = 16;
+  constexpr int ROWS = 8;
   const int kthreads = vec ? K / 4 : K;
   dim3 grid((kthreads + 127) / 128, (M + ROWS - 1) / ROWS);
   NT_DISPATCH(N, {
@@ -434,13 +673,18 @@ int skinny_bwd_weight(b200_ctx *ctx, int M, int N, int K, const float *dY, int l
   const bool vec = (K % 4 == 0) && (ldx % 4 == 0) && al16(X);
   dim3 grid((K + (vec ? 127 : 31)) / (vec ? 128 : 32), chunks);
   NT_DISPATCH(N, {
-    if (vec) skinny_wgrad_partial_kernel<NT, ROWS, true><<<grid, 256, 0, ctx->stream>>>(M, N, K, dY, lddy, X, ldx, part, db ? part_b : nullptr);
-    else skinny_wgrad_partial_kernel<NT, ROWS, false><<<grid, 256, 0, ctx->stream>>>(M, N, K, dY, lddy, X, ldx, part, db ? part_b : nullptr);
+    if (vec) {
+      PREFER_MAX_SMEM_ONCE((skinny_wgrad_partial_kernel<NT, ROWS, true>));
+      skinny_wgrad_partial_kernel<NT, ROWS, true><<<grid, 256, 0, ctx->stream>>>(M, N, K, dY, lddy, X, ldx, part, db ? part_b : nullptr);
+    } else {
+      skinny_wgrad_partial_kernel<NT, ROWS, false><<<grid, 256, 0, ctx->stream>>>(M, N, K, dY, lddy, X, ldx, part, db ? part_b : nullptr);
+    }
   });
   LAUNCH_CHECK(ctx);
   ReduceJob j0{part, dW, (int)nk, lddw, K};
   ReduceJob j1{part_b, db, db ? N : 0, 1, 1};
   dim3 rgrid((unsigned)((nk + 255) / 256), db ? 2 : 1);
+  PREFER_MAX_SMEM_ONCE(reduce_partials_kernel);
   reduce_partials_kernel<<<rgrid, 256, 0, ctx->stream>>>(chunks, scale, beta, j0, j1);
   LAUNCH_CHECK(ctx);
   return B200_OK;
@@ -454,13 +698,16 @@ int colsum_scaled(b200_ctx *ctx, int M, int N, const float *dy, int ld, float sc
   const bool vec = (N % 4 == 0) && (ld % 4 == 0) && al16(dy);
   if (vec) {
     dim3 grid((N + 127) / 128, chunks);
+    PREFER_MAX_SMEM_ONCE((colsum_partial_kernel<ROWS, true>));
     colsum_partial_kernel<ROWS, true><<<grid, 256, 0, ctx->stream>>>(M, N, dy, ld, part);
   } else {
     dim3 grid((N + 31) / 32, chunks);
+    PREFER_MAX_SMEM_ONCE((colsum_partial_kernel<ROWS, false>));
     colsum_partial_kernel<ROWS, false><<<grid, 256, 0, ctx->stream>>>(M, N, dy, ld, part);
   }
   LAUNCH_CHECK(ctx);
   ReduceJob j0{part, out, N, 1, 1};
+  PREFER_MAX_SMEM_ONCE(reduce_partials_kernel);
   reduce_partials_kernel<<<dim3((N + 255) / 256, 1), 256, 0, ctx->stream>>>(chunks, scale, beta, j0, j0);
   LAUNCH_CHECK(ctx);
   return B200_OK;

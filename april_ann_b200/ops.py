@@ -173,6 +173,25 @@ def log_softmax_mcce_fused(logits, target, ctx=None):
     return logp.numpy(), rows.numpy(), grad.numpy()
 
 
+def output_layer_fused(X, W, bias, target, act_prev=None, want_dx=True, ctx=None):
+    """dot_product + bias + log_softmax + MCCE rows + gradient + data gradient of the layer below in one
+    launch -> (logits, logp, loss rows, grad, dX or None)."""
+    ctx = ctx or get_context()
+    X, W, target = (np.ascontiguousarray(a, _f32) for a in (X, W, target))
+    M, K = X.shape
+    N = W.shape[0]
+    d_x, d_w, d_t = _dev(ctx, X), _dev(ctx, W), _dev(ctx, target)
+    d_b = _dev(ctx, np.ascontiguousarray(bias, _f32).reshape(-1)) if bias is not None else None
+    logits, logp, rows, grad = (DeviceArray(ctx, (M, N)), DeviceArray(ctx, (M, N)), DeviceArray(ctx, (M,)),
+                                DeviceArray(ctx, (M, N)))
+    dx = DeviceArray(ctx, (M, K)) if want_dx else None
+    check(lib.b200_output_layer_fused(ctx.h, C.c_int(M), C.c_int(N), C.c_int(K), d_x.ptr, C.c_int(K), d_w.ptr, C.c_int(K),
+                                      d_b.ptr if d_b is not None else None, d_t.ptr, logits.ptr, logp.ptr, rows.ptr,
+                                      grad.ptr, C.c_int(ACT[act_prev] if act_prev else 0), dx.ptr if dx is not None else None,
+                                      C.c_int(K)))
+    return logits.numpy(), logp.numpy(), rows.numpy(), grad.numpy(), (dx.numpy() if dx is not None else None)
+
+
 def conv2d_fwd(x, w, kernel, step=(1, 1), bias=None, act=None, ctx=None):
     ctx = ctx or get_context()
     x, w = np.ascontiguousarray(x, _f32), np.ascontiguousarray(w, _f32)

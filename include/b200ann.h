@@ -76,6 +76,21 @@ int b200_memcpy_h2d(b200_ctx *ctx, void *dst, const void *src, size_t bytes);  /
 int b200_memcpy_d2h(b200_ctx *ctx, void *dst, const void *src, size_t bytes);  /* async on the stream */
 int b200_memcpy_d2d(b200_ctx *ctx, void *dst, const void *src, size_t bytes);
 int b200_memset_zero(b200_ctx *ctx, void *dst, size_t bytes);
+/* Side branches of a training step.  The reference runs one kernel after another on stream 0
+ * (packages/basics/mathcore/c_src/gpu_helper.cu:28-35); here the work that is not on the critical
+ * path of a step (weight gradients, per-tensor SGD, loss statistics) is issued on side streams and
+ * becomes parallel branches of the step's CUDA graph.
+ *   b200_branch_begin(i)   until b200_branch_end, launches go to side stream i, ordered after what
+ *                          the main stream holds now
+ *   b200_branch_wait(i)    the current stream waits for what side stream i holds now
+ *   b200_branch_join_all   the main stream waits for every open branch (call before the step ends)
+ *   b200_set_sm_budget     SMs one persistent contraction may plan for when two of them are meant
+ *                          to run side by side (0 = the whole device) */
+int b200_branch_begin(b200_ctx *ctx, int branch);
+int b200_branch_end(b200_ctx *ctx);
+int b200_branch_wait(b200_ctx *ctx, int branch);
+int b200_branch_join_all(b200_ctx *ctx);
+int b200_set_sm_budget(b200_ctx *ctx, int sms);
 /* CUDA-event timing on the compute stream (bench / roofline) */
 int b200_event_create(void **ev);
 int b200_event_destroy(void *ev);
@@ -155,6 +170,17 @@ int b200_log_softmax_mcce_fused(b200_ctx *ctx, int M, int C, const float *logits
  * stats[0] += sum(rows), stats[1] += sum(rows^2), stats[2] += M   (float64 on the device) */
 int b200_loss_accumulate(b200_ctx *ctx, int M, const float *loss_rows, double *stats);
 
+/* Output layer of a classifier in one launch (N <= 16 classes, K % 4 == 0): the dot_product + bias forward
+ * (dot_product_component.cc:63-98, bias_component.cc:46-73), log_softmax
+ * (activation_function_kernels.cu:289-325), the multi-class cross-entropy rows and gradient
+ * (loss_kernels.cu:171-185, multiclass_cross_entropy_loss_function.cc:61-71) and the data gradient of the
+ * layer below, dX = (grad . W) (.) act'(X) with X that layer's activation output
+ * (dot_product_component.cc:123-152 + the actf derivative).  logits / logp / loss_rows / grad / dX may be
+ * NULL.  Returns B200_ERR_UNSUPPORTED for shapes it does not cover. */
+int b200_output_layer_fused(b200_ctx *ctx, int M, int N, int K, const float *X, int ldx, const float *W, int ldw,
+                            const float *bias, const float *target, float *logits, float *logp,
+                            float *loss_rows, float *grad, int dact, float *dX, int lddx);
+
 /* ------------------------------------------------------------------ SGD
  * replaces ann.optimizer.sgd:execute (packages/ann/optimizer/lua_src/optimizer_sgd.lua:50-100)
  * and its helpers (base_optimizer.lua:28-49).  One launch updates every tensor:
@@ -172,6 +198,14 @@ typedef struct {
 int b200_sgd_multi_tensor(b200_ctx *ctx, int ntensors, const b200_sgd_tensor *tensors_dev,
                           const b200_sgd_tensor *tensors_host, double decay,
                           const int64_t *count_dev, int write_back_grad);
+/* same; flags bit 0 = write the regularised gradient back, bit 1 = this is the last update launch of
+ * the step: its last CTA to finish adds 1 to count_dev[0] (count_dev[1] is the ticket word, zero
+ * between launches), which replaces a separate counter launch */
+#define B200_SGD_WRITE_BACK_GRAD 1
+#define B200_SGD_INCREMENT_COUNT 2
+int b200_sgd_multi_tensor_ex(b200_ctx *ctx, int ntensors, const b200_sgd_tensor *tensors_dev,
+                             const b200_sgd_tensor *tensors_host, double decay, int64_t *count_dev,
+                             int flags);
 int b200_counter_increment(b200_ctx *ctx, int64_t *count_dev);
 
 /* ------------------------------------------------------------------ convolution / pooling

@@ -207,6 +207,32 @@ def test_fused_log_softmax_mcce(ops, C):
     assert np.allclose(grad, l.gradient(want_logp, t), atol=3e-7)
 
 
+@pytest.mark.parametrize("M,N,K,act", [(64, 10, 2048, "relu"), (37, 3, 512, "tanh"), (8, 16, 1028, "logistic"),
+                                       (1, 10, 64, None)])
+def test_output_layer_fused_launch(ops, M, N, K, act):
+    """dot_product + bias + log_softmax + MCCE + gradient + data gradient of the layer below, one launch,
+    against the oracle's component-by-component result (ragged row counts, every N padding class)."""
+    h = rnd_mat(40, M, K)
+    if act:
+        h = {"relu": A.relu, "tanh": A.antisym_logistic, "logistic": A.logistic}[act](h)
+    w, b = rnd_mat(41, N, K, lo=-0.1, hi=0.1), rnd_mat(42, N)
+    t = np.zeros((M, N), dtype=np.float32)
+    t[np.arange(M), (np.arange(M) * 5) % N] = 1.0
+    logits, logp, rows, grad, dx = ops.output_layer_fused(h, w, b, t, act_prev=act)
+    want_logits = (h.astype(np.float64) @ w.astype(np.float64).T + b).astype(np.float32)
+    assert rel_l2(logits, want_logits) < F32_TOL
+    want_logp = A.log_softmax_rows(want_logits)
+    l = A.MultiClassCrossEntropy()
+    assert np.allclose(logp, want_logp, atol=2e-5)
+    assert np.allclose(rows, l.loss_rows(want_logp, t), rtol=2e-5, atol=2e-5)
+    want_grad = l.gradient(want_logp, t)
+    assert np.allclose(grad, want_grad, atol=2e-6)
+    want_dx = want_grad.astype(np.float64) @ w.astype(np.float64)
+    if act:
+        want_dx = want_dx * {"relu": A.relu_der, "tanh": A.antisym_logistic_der, "logistic": A.logistic_der}[act](h)
+    assert rel_l2(dx, want_dx.astype(np.float32)) < 2e-5
+
+
 # ------------------------------------------------------------------ convolution / pooling
 @pytest.mark.parametrize("B,C,H,W,n,kh,kw,sh,sw", [(3, 1, 16, 16, 10, 3, 3, 1, 1), (2, 10, 7, 7, 20, 2, 2, 1, 1),
                                                    (4, 3, 12, 11, 5, 5, 4, 2, 3), (2, 16, 12, 12, 32, 5, 5, 1, 1)])

@@ -1,0 +1,59 @@
+"""Timeline of one replayed C2 training step (GPU box): kernel start / duration / stream from CUPTI
+through torch.profiler (the kernels are this library's; torch only hosts the profiler).
+
+    python tools/step_trace.py [steps]
+Prints the kernels of the last profiled step in start order, relative to the step's first kernel."""
+import json
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+from torch.profiler import ProfilerActivity, profile  # noqa: E402
+
+import april_ann_b200 as ann  # noqa: E402
+import bench  # noqa: E402
+
+torch.cuda.init()
+torch.zeros(1, device="cuda")
+ctx = ann.get_context(0)
+ctx.set_math_mode(ann.MATH_TF32)
+topo = os.environ.get("TOPOLOGY", bench.TOPOLOGY)
+bunch = int(os.environ.get("BUNCH", bench.BUNCH))
+tr = ann.trainable.supervised_trainer(ann.mlp.all_all.generate(topo), ann.loss.multi_class_cross_entropy(), bunch, ctx=ctx)
+tr.build()
+tr.set_option("learning_rate", 0.01)
+tr.set_option("momentum", 0.9)
+tr.set_option("weight_decay", 1e-4)
+tr.set_layerwise_option("b.", "weight_decay", 0)
+tr.randomize_weights(random=ann.random(1234), inf=-1, sup=1, use_fanin=True, use_fanout=True)
+sizes = [int(v) for v in topo.split() if v.isdigit()]
+rng = np.random.RandomState(1)
+x = rng.uniform(-1, 1, (bunch, sizes[0])).astype(np.float32)
+t = np.zeros((bunch, sizes[-1]), np.float32)
+t[np.arange(bunch), rng.randint(0, sizes[-1], bunch)] = 1
+tr.stage(x, t, bunch)
+for _ in range(6):
+    tr.step_staged(bunch)
+ctx.sync()
+steps = int(sys.argv[1]) if len(sys.argv) > 1 else 4
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    for _ in range(steps):
+        tr.step_staged(bunch)
+    ctx.sync()
+path = os.path.join(tempfile.mkdtemp(), "trace.json")
+prof.export_chrome_trace(path)
+ev = [e for e in json.load(open(path))["traceEvents"] if e.get("cat") == "kernel"]
+ev.sort(key=lambda e: e["ts"])
+# split into steps at the first forward kernel: steps are equal-length runs
+n = len(ev) // steps
+last = ev[-n:]
+t0 = last[0]["ts"]
+print("%d kernels per step; step span %.1f us" % (n, last[-1]["ts"] + last[-1]["dur"] - t0))
+for e in last:
+    a = e.get("args", {})
+    print("%8.1f +%6.1f  s%-3s grid %-14s %s" % (e["ts"] - t0, e["dur"], a.get("stream", "?"), str(a.get("grid", "")), e["name"][:90]))
