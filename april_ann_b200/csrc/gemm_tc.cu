@@ -228,7 +228,7 @@ struct Staging {
 template <int ACT, int DACT>
 __device__ __forceinline__ void epilogue_tile(const TcParams &p, const CUtensorMap *map_c, uint32_t taddr, const Staging &stg,
                                               int m_base, int n0, int lane, int &issued, int c_begin, int c_end,
-                                              uint32_t recv, uint32_t bias_smem) {
+                                              uint32_t recv, uint32_t bias_smem, const uint32_t (&relu_mask)[8], bool have_mask) {
   const float alpha = p.ep.alpha, beta = p.ep.beta;
   const float *__restrict__ dsrc = p.ep.dsrc;
   const int ld_dsrc = p.ep.ld_dsrc, ldc = p.ldc, M = p.M;
@@ -242,7 +242,9 @@ __device__ __forceinline__ void epilogue_tile(const TcParams &p, const CUtensorM
   const bool d_vec = !has_d || (((ld_dsrc & 3) == 0) && ((((uintptr_t)dsrc) & 15) == 0));
   // simple epilogues (alpha, bias, activation) are applied in the accumulator layout (lane = row);
   // the ones that read global memory per element (derivative source, old C) run after the transpose
-  const bool simple = tma_store && !has_d && !has_c;
+  // (ReLU derivatives arrive as per-chunk bit masks in the accumulator layout: simple as well)
+  const bool masked = (DACT == B200_ACT_RELU) && have_mask && !has_bias;
+  const bool simple = tma_store && !has_c && (!has_d || masked);
   // bring-up: phase durations of warp 2 lane 0, accumulated in registers, flushed once at the end
   const bool timing = p.stamps != nullptr && (p.dbg_flags & 32u) && threadIdx.x == 64;   // per-phase clocks perturb the epilogue: opt-in
   long long tacc[6] = {0, 0, 0, 0, 0, 0};
@@ -277,7 +279,16 @@ __device__ __forceinline__ void epilogue_tile(const TcParams &p, const CUtensorM
       }
     }
     EPI_STAMP(2);
-    if (simple) {
+    if (simple && masked) {
+      // chunk index within this warp's range selects the mask (unrolled select keeps the array in registers)
+      const int q = (c0 - c_begin) >> 5;
+      uint32_t mk = 0u;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) mk = (i == q) ? relu_mask[i] : mk;
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        r[j] = ((mk >> j) & 1u) ? __float_as_uint(alpha * __uint_as_float(r[j])) : 0u;
+    } else if (simple) {
       if (has_bias) {
         // the tile's bias slice was staged in shared memory before the accumulator was ready:
         // 8 broadcast float4 reads per chunk, no global latency on this path
@@ -549,6 +560,53 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         epi_bar_sync();
       }
+      // ReLU data gradients: the derivative is one bit per element.  While the contraction is still running
+      // this warp reads the activation tile of the layer below for the chunks it will finish (lane = its
+      // accumulator row, 8 x 16 bytes per chunk) and keeps one 32-bit mask per chunk, so that the epilogue
+      // needs no global load and stays in the accumulator layout.  (Loading those values inside the
+      // epilogue, after the transpose, cost ~5500 cycles per 32x32 chunk of exposed latency.)
+      uint32_t relu_mask[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+      bool have_mask = false;
+      if (p.ep.dact == B200_ACT_RELU && p.tma_store && p.ep.beta == 0.0f && p.BN <= 256) {
+        have_mask = true;
+        const int nch_p = (p.BN + 31) >> 5;
+        int lo = 0, hi = nch_p;
+        if (p.splitk == 2) {
+          const int own0 = (nch_p + 1) >> 1;
+          lo = crank ? own0 : 0;
+          hi = crank ? nch_p : own0;
+        }
+        if (tile + tile_step >= num_tiles) {
+          const int mid = lo + ((hi - lo + 1) >> 1);
+          if (half) lo = mid; else hi = mid;
+        } else if (half) {
+          lo = hi;
+        }
+        const int row = m0 + quad * 32 + lane;
+        const float *drow = p.ep.dsrc + (size_t)min(row, p.M - 1) * p.ep.ld_dsrc + n0;
+        const bool vec = ((p.ep.ld_dsrc & 3) == 0) && ((((uintptr_t)p.ep.dsrc) & 15) == 0) && ((n0 & 3) == 0);
+        const int n_lim = min(p.N - n0, p.BN);          // valid columns of this tile
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int ch = lo + q;
+          if (ch < hi) {
+            uint32_t mk = 0u;
+            if (vec && ch * 32 + 32 <= n_lim) {
+              float4 v[8];
+#pragma unroll
+              for (int g = 0; g < 8; ++g) v[g] = __ldg(reinterpret_cast<const float4 *>(drow + ch * 32 + 4 * g));
+#pragma unroll
+              for (int g = 0; g < 8; ++g)
+                mk |= ((v[g].x > 0.0f ? 1u : 0u) | (v[g].y > 0.0f ? 2u : 0u) | (v[g].z > 0.0f ? 4u : 0u) |
+                       (v[g].w > 0.0f ? 8u : 0u)) << (4 * g);
+            } else {
+              for (int j = 0; j < 32; ++j)
+                if (ch * 32 + j < n_lim && __ldg(drow + ch * 32 + j) > 0.0f) mk |= 1u << j;
+            }
+            relu_mask[q] = mk;
+          }
+        }
+      }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       if (stamp && threadIdx.x == 64) stamp[5] = clock64();
@@ -618,6 +676,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         stg.stride = (uint32_t)(EPI_WARPS * 4096);
         stg.nbuf = min(4, avail);
         if (avail < 1) {   // cannot happen with the rings gemm_tc() sizes; stay correct anyway
+          have_mask = false;   // the masks were gathered for the split ranges
           w_lo = half ? ch_hi : ch_lo;
           w_hi = ch_hi;
           stg.base = staging + (uint32_t)quad * 4096u;
@@ -636,7 +695,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int c_begin = w_lo * 32, c_end = min(w_hi * 32, p.BN);
       // the activation / derivative kind is a compile-time constant inside each instantiation: a run-time
       // switch per element made the unrolled epilogue ~4500 instructions per 32-column chunk
-#define EPI_CALL(A, D) epilogue_tile<A, D>(p, &map_c, taddr, stg, m0 + quad * 32, n0, lane, issued, c_begin, c_end, recv, bias_smem)
+#define EPI_CALL(A, D) epilogue_tile<A, D>(p, &map_c, taddr, stg, m0 + quad * 32, n0, lane, issued, c_begin, c_end, recv, bias_smem, relu_mask, have_mask)
       if (p.ep.dact != B200_ACT_NONE) {
         switch (p.ep.dact) {
           case B200_ACT_LOGISTIC: EPI_CALL(B200_ACT_NONE, B200_ACT_LOGISTIC); break;

@@ -262,7 +262,9 @@ class StackANNComponent : public ANNComponent {
   // the main stream; on_backprop_issued(component) fires once the component's own data gradient has
   // been issued, i.e. when nothing later in the step reads its weights any more.
   bool use_branches = false;
-  bool concurrent_contractions = true;   // dgrad and wgrad of a layer side by side, half the SMs each
+  // dgrad / wgrad of a layer: 1 = side by side, half the SMs each; 2 = one after the other, full width
+  // (the weight gradient still on its branch); 0 = both full width at once
+  int contraction_mode = 1;
   std::function<void(ANNComponent *, int branch)> on_backprop_issued;
   void prepareGradScales();   // sets grad_scale of every weight-bearing component from grad_bunch
   const std::vector<ANNComponent *> &flatComponents() const { return flat; }
@@ -358,6 +360,7 @@ class SupervisedTrainer {
   bool keep_gradients = false;    // write the regularised gradient back (observable grads; +4 B/param)
   bool use_cuda_graph = true;
   bool use_branches = true;       // single replica: weight gradients / updates / statistics on side branches
+  bool sgd_as_ready = true;       // single replica: update each big tensor as soon as it is ready (false: one launch at the end)
   bool fuse_output_layer = true;  // <=16-class output layer + log_softmax + MCCE + data gradient in one launch
   MatrixDict weights_table, grads, updates;
   std::vector<std::string> weights_order;   // sorted names (initialisation / API order)
@@ -376,6 +379,11 @@ class SupervisedTrainer {
   size_t total_params = 0;
   b200_sgd_tensor *sgd_dev = nullptr;
   std::vector<b200_sgd_tensor> sgd_host;
+  // single replica: the tensors of the big contractions are updated one launch each, as soon as they are
+  // ready; all the others (biases, the output layer) in one launch over this second table
+  b200_sgd_tensor *sgd_light_dev = nullptr;
+  std::vector<b200_sgd_tensor> sgd_light_host;
+  std::vector<char> tensor_heavy;   // by arena index
   bool sgd_dirty = true;
   std::string sgd_signature;
   // staging + device-resident dataset

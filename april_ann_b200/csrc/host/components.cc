@@ -493,35 +493,51 @@ MatrixPtr StackANNComponent::doBackprop(const MatrixPtr &err) {
   while (i >= 0) {
     ANNComponent *c = flat[i];
     int branch = -1;
-    bool had_grads = false;
+    bool had_grads = false, deferred = false;
     if (interleave_grads && c->hasWeightsName() && cur) {
       had_grads = true;
       // the error input of this component is final: its weight gradients can be computed now
       c->error_input = cur;
-      if (use_branches) {
-        auto *d = dynamic_cast<DotProductANNComponent *>(c);
-        const bool heavy = (d && d->getOutputSize() > 16) || dynamic_cast<ConvolutionANNComponent *>(c);
-        branch = heavy ? 2 : 1;
-        check(b200_branch_begin(ctx, branch));
-        // a layer's weight gradient (branch) and data gradient (main stream) are independent: plan each
-        // persistent contraction for half of the SMs so that they really run side by side
-        if (d && heavy && concurrent_contractions && !(i == 0 && skip_input_gradient)) {
-          int sms = 0;
-          check(b200_sm_count(ctx, &sms));
-          check(b200_set_sm_budget(ctx, sms / 2));
+      auto *d = dynamic_cast<DotProductANNComponent *>(c);
+      const bool heavy = (d && d->getOutputSize() > 16) || dynamic_cast<ConvolutionANNComponent *>(c);
+      const bool has_dgrad = d && heavy && !(i == 0 && skip_input_gradient);
+      if (use_branches) branch = heavy ? 2 : 1;
+      if (use_branches && has_dgrad && contraction_mode == 2) {
+        // full-width contractions one after the other: the weight gradient is issued (on its branch) right
+        // after the data gradient of this iteration, see Issued below
+        deferred = true;
+      } else {
+        if (use_branches) {
+          check(b200_branch_begin(ctx, branch));
+          // a layer's weight gradient (branch) and data gradient (main stream) are independent: plan each
+          // persistent contraction for half of the SMs so that they really run side by side
+          // (also when no data gradient follows: the update of the previous layer's tensor runs beside
+          // this contraction, on the other half of the SMs)
+          if (d && heavy && contraction_mode == 1) {
+            int sms = 0;
+            check(b200_sm_count(ctx, &sms));
+            check(b200_set_sm_budget(ctx, sms / 2));
+          }
         }
+        c->computeAllGradients(*interleave_grads);
+        if (on_gradients_ready) on_gradients_ready(c);
+        if (use_branches) check(b200_branch_end(ctx));
       }
-      c->computeAllGradients(*interleave_grads);
-      if (on_gradients_ready) on_gradients_ready(c);
-      if (use_branches) check(b200_branch_end(ctx));
     }
     struct Issued {   // fires on every way out of this iteration
-      StackANNComponent *s; ANNComponent *c; int branch; bool had_grads;
+      StackANNComponent *s; ANNComponent *c; int branch; bool had_grads, deferred;
       ~Issued() noexcept(false) {
         if (s->use_branches) b200_set_sm_budget(s->ctx, 0);
-        if (had_grads && s->on_backprop_issued && !std::uncaught_exceptions()) s->on_backprop_issued(c, branch);
+        if (std::uncaught_exceptions()) return;
+        if (deferred) {
+          check(b200_branch_begin(s->ctx, branch));
+          c->computeAllGradients(*s->interleave_grads);
+          if (s->on_gradients_ready) s->on_gradients_ready(c);
+          check(b200_branch_end(s->ctx));
+        }
+        if (had_grads && s->on_backprop_issued) s->on_backprop_issued(c, branch);
       }
-    } issued{this, c, branch, had_grads};
+    } issued{this, c, branch, had_grads, deferred};
     if (fuse) {
       auto *la = dynamic_cast<ActivationFunctionANNComponent *>(c);
       if (la && i == n - 1 && last_actf_backprop_is_identity) {

@@ -145,7 +145,8 @@ SupervisedTrainer::SupervisedTrainer(b200_ctx *ctx, const std::shared_ptr<StackA
   // tuning switches (A/B measurements): side branches of the step, and dgrad || wgrad of a layer
   if (const char *e = getenv("B200_BRANCHES")) use_branches = atoi(e) != 0;
   if (const char *e = getenv("B200_FUSE_OUTPUT")) fuse_output_layer = atoi(e) != 0;
-  if (const char *e = getenv("B200_CONCURRENT_BWD")) net->concurrent_contractions = atoi(e) != 0;
+  if (const char *e = getenv("B200_SGD_AS_READY")) sgd_as_ready = atoi(e) != 0;
+  if (const char *e = getenv("B200_CONCURRENT_BWD")) net->contraction_mode = atoi(e);
   void *p;
   check(b200_malloc(ctx, &p, 2 * sizeof(int64_t)));
   count_dev = (int64_t *)p;
@@ -164,6 +165,7 @@ SupervisedTrainer::~SupervisedTrainer() {
   }
   if (count_dev) b200_free(ctx, count_dev);
   if (sgd_dev) b200_free(ctx, sgd_dev);
+  if (sgd_light_dev) b200_free(ctx, sgd_light_dev);
 }
 
 void SupervisedTrainer::build(unsigned input, unsigned output) {
@@ -288,7 +290,27 @@ void SupervisedTrainer::uploadSgdTable() {
     sgd_dev = (b200_sgd_tensor *)p;
   }
   check(b200_memcpy_h2d(ctx, sgd_dev, sgd_host.data(), sizeof(b200_sgd_tensor) * (size_t)nt));
-  check(b200_sync(ctx));  // sgd_host may be rewritten before the copy would otherwise run
+  // heavy = written by a big contraction (dot_product with more than 16 outputs, convolution)
+  tensor_heavy.assign(nt, 0);
+  for (auto *c : net->flatComponents()) {
+    if (!c->hasWeightsName()) continue;
+    auto *d = dynamic_cast<DotProductANNComponent *>(c);
+    const bool heavy = (d && d->getOutputSize() > 16) || dynamic_cast<ConvolutionANNComponent *>(c);
+    if (!heavy) continue;
+    for (int i = 0; i < nt; ++i)
+      if (arena_order[i] == c->getWeightsName()) tensor_heavy[i] = 1;
+  }
+  sgd_light_host.clear();
+  for (int i = 0; i < nt; ++i)
+    if (!tensor_heavy[i]) sgd_light_host.push_back(sgd_host[i]);
+  if (!sgd_light_dev) {
+    void *p;
+    check(b200_malloc(ctx, &p, sizeof(b200_sgd_tensor) * (size_t)std::max(nt, 1)));
+    sgd_light_dev = (b200_sgd_tensor *)p;
+  }
+  if (!sgd_light_host.empty())
+    check(b200_memcpy_h2d(ctx, sgd_light_dev, sgd_light_host.data(), sizeof(b200_sgd_tensor) * sgd_light_host.size()));
+  check(b200_sync(ctx));  // the host tables may be rewritten before the copies would otherwise run
   sgd_dirty = false;
   // captured graphs read the hyper-parameters from the device table, but the max-norm launches
   // are part of the graph structure: re-capture when that set changes
@@ -441,57 +463,65 @@ void SupervisedTrainer::runStep(const MatrixPtr &x, const MatrixPtr &t, int glob
     }
     loss.accumLoss(rows);
   } else {
-    // Single replica: the loss statistics, the weight gradients and the update of every finished tensor
-    // run on side branches; only the data gradients stay on the critical path.  The update of a tensor
-    // is issued once its gradient is final AND the data gradient that reads the weights has been
-    // issued (on_backprop_issued).  It is held back by one tensor so that the very last one can run on
-    // the main stream after the join and bump the step counter.
+    // Single replica: the loss statistics, the weight gradients and the updates run on side branches;
+    // only the data gradients stay on the critical path.  The tensor of a big contraction is updated by
+    // its own launch as soon as its gradient is final AND the data gradient that reads the weights has
+    // been issued (on_backprop_issued): on branch 0, beside the next contraction -- except the last one of
+    // the step, which stays on the branch of its gradient kernel.  All the small tensors (biases, output
+    // layer) take one launch at the end of branch 1, behind their gradient kernels.
     if (use_branches) check(b200_branch_begin(ctx, 0));
     loss.accumLoss(rows);
     if (use_branches) check(b200_branch_end(ctx));
-    int pending = -1, pending_branch = -1;
-    auto issuePending = [&](bool last) {
-      if (pending < 0) return;
-      // updates have their own branch (0): they never sit in front of the next gradient kernel of
-      // branch 1 / 2; they wait for the branch that produced the gradient.  The last one of the step goes
-      // to the branch of its own gradient kernel instead (nothing else will be issued there), so that it
-      // does not queue behind the big update still running on branch 0.
-      if (use_branches) {
-        const int b = (last && pending_branch > 0) ? pending_branch : 0;
-        check(b200_branch_begin(ctx, b));
-        if (pending_branch > 0 && pending_branch != b) check(b200_branch_wait(ctx, pending_branch));
-      }
-      const bool bump = last && !use_branches;   // serial flow: the last update launch bumps the step counter
-      check(b200_sgd_multi_tensor_ex(ctx, 1, sgd_dev + pending, sgd_host.data() + pending, decay, count_dev,
-                                     wb | (bump ? B200_SGD_INCREMENT_COUNT : 0)));
-      if (use_branches) check(b200_branch_end(ctx));
-      done[pending] = 1;
-      pending = -1;
-    };
+    ANNComponent *first_heavy = nullptr;   // its tensor is the last one of the backward pass
+    for (auto *c : net->flatComponents()) {
+      if (!c->hasWeightsName()) continue;
+      const int i = tensorIndex(c->getWeightsName());
+      if (i >= 0 && tensor_heavy[i]) { first_heavy = c; break; }
+    }
     net->use_branches = use_branches;
     net->on_backprop_issued = [&](ANNComponent *c, int branch) {
       if (!isFinalContribution(c)) return;
       const int i = tensorIndex(c->getWeightsName());
-      if (i < 0 || done[i] || i == pending) return;
-      issuePending(false);
-      pending = i;
-      pending_branch = branch;
+      if (i < 0 || done[i] || !tensor_heavy[i] || !sgd_as_ready) return;
+      if (use_branches) {
+        const int b = (c == first_heavy && branch > 0) ? branch : 0;
+        check(b200_branch_begin(ctx, b));
+        if (branch > 0 && branch != b) check(b200_branch_wait(ctx, branch));
+      }
+      // an update that will run beside the next weight-gradient contraction (which plans for half of the
+      // SMs, see StackANNComponent::doBackprop) takes the other half; the last one has the device to itself
+      if (use_branches && c != first_heavy && net->contraction_mode == 1) {
+        int sms = 0;
+        check(b200_sm_count(ctx, &sms));
+        check(b200_set_sm_budget(ctx, sms - sms / 2));
+      }
+      check(b200_sgd_multi_tensor_ex(ctx, 1, sgd_dev + i, sgd_host.data() + i, decay, count_dev, wb));
+      check(b200_set_sm_budget(ctx, 0));
+      if (use_branches) check(b200_branch_end(ctx));
+      done[i] = 1;
     };
     try {
       net->doBackprop(grad);
-      // tensors no component touched this step (zero gradient) still take their momentum / decay step
-      for (int i = 0; i < nt; ++i) {
-        if (done[i] || i == pending) continue;
-        issuePending(false);
-        pending = i;
-        pending_branch = 1;
+      // heavy tensors no component touched this step (zero gradient) still take their momentum / decay step
+      if (!sgd_as_ready) {
+        // everything in one launch once every gradient exists
+        check(b200_branch_join_all(ctx));
+        check(b200_sgd_multi_tensor_ex(ctx, nt, sgd_dev, sgd_host.data(), decay, count_dev, wb | B200_SGD_INCREMENT_COUNT));
       }
-      const bool had_pending = pending >= 0;
-      issuePending(true);
+      for (int i = 0; i < nt && sgd_as_ready; ++i) {
+        if (done[i] || !tensor_heavy[i]) continue;
+        check(b200_sgd_multi_tensor_ex(ctx, 1, sgd_dev + i, sgd_host.data() + i, decay, count_dev, wb));
+        done[i] = 1;
+      }
+      if (sgd_as_ready && !sgd_light_host.empty()) {
+        if (use_branches) check(b200_branch_begin(ctx, 1));
+        check(b200_sgd_multi_tensor_ex(ctx, (int)sgd_light_host.size(), sgd_light_dev, sgd_light_host.data(), decay,
+                                       count_dev, wb));
+        if (use_branches) check(b200_branch_end(ctx));
+      }
       check(b200_branch_join_all(ctx));
-      // with branches the updates of a step run on several streams: the counter is bumped once they have
-      // all been joined
-      if (use_branches || !had_pending) check(b200_counter_increment(ctx, count_dev));
+      // the updates ran on several streams: bump the counter once they are joined
+      if (sgd_as_ready) check(b200_counter_increment(ctx, count_dev));
     } catch (...) {
       cleanup();
       b200_branch_join_all(ctx);

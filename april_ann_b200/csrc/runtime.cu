@@ -61,7 +61,9 @@ extern "C" int b200_create(int device, b200_ctx **out) {
   CUDA_TRY(cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_greatest));
   ctx->main_stream = ctx->stream;
   for (int i = 0; i < b200_ctx::kBranches; ++i) {
-    CUDA_TRY(cudaStreamCreateWithPriority(&ctx->side_stream[i], cudaStreamNonBlocking, prio_least));
+    // branch 2 (the big weight-gradient contractions) outranks branches 0 / 1 (updates, light gradients)
+    const int prio = (i == 2 && prio_greatest < prio_least - 1) ? prio_greatest + 1 : prio_least;
+    CUDA_TRY(cudaStreamCreateWithPriority(&ctx->side_stream[i], cudaStreamNonBlocking, prio));
     CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_fork[i], cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_side[i], cudaEventDisableTiming));
   }

@@ -18,11 +18,19 @@
 
 namespace {
 
-constexpr int TPB = 128;
+constexpr int TPB = 128;          // light launches (small tensors, many tensors per launch)
+constexpr int TPB_BIG = 1024;     // one big tensor: one CTA per SM
 constexpr int UNROLL = 4;
+// A big-tensor CTA asks for more (unused) dynamic shared memory than half an SM, so that exactly one is
+// resident per SM and none fits beside a contraction CTA: an update that runs next to a contraction then
+// owns the SMs the contraction leaves free (ctx->sm_budget tells how many) instead of sharing SMs with it.
+// Sharing was measured: the co-resident update competes for the SM's path to L2 and slowed the
+// weight-gradient contraction from 17 to 31 us.
+constexpr int SGD_BIG_SMEM = 120 * 1024;
 
-__global__ void __launch_bounds__(TPB, 8) sgd_kernel(const b200_sgd_tensor *__restrict__ tensors, double decay,
-                                                  int64_t *count_dev, int flags) {
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 65536 / (64 * THREADS)) sgd_kernel(const b200_sgd_tensor *__restrict__ tensors, double decay,
+                                                                           int64_t *count_dev, int flags) {
   const b200_sgd_tensor t = tensors[blockIdx.y];
   const int64_t count = *reinterpret_cast<volatile int64_t *>(count_dev);
   const int write_back_grad = flags & B200_SGD_WRITE_BACK_GRAD;
@@ -63,13 +71,14 @@ __global__ void __launch_bounds__(TPB, 8) sgd_kernel(const b200_sgd_tensor *__re
     for (; i + (UNROLL - 1) * nth < n4; i += UNROLL * nth) {
       float4 w[UNROLL], g[UNROLL], u[UNROLL];
 #pragma unroll
-      for (int j = 0; j < UNROLL; ++j) { w[j] = w4[i + j * nth]; g[j] = g4[i + j * nth]; u[j] = u4[i + j * nth]; }
+      // w stays in L2 for the next forward pass; g and u are touched once per step: streaming loads / stores
+      for (int j = 0; j < UNROLL; ++j) { w[j] = w4[i + j * nth]; g[j] = __ldcs(g4 + i + j * nth); u[j] = __ldcs(u4 + i + j * nth); }
 #pragma unroll
       for (int j = 0; j < UNROLL; ++j) {
         upd(w[j].x, g[j].x, u[j].x); upd(w[j].y, g[j].y, u[j].y); upd(w[j].z, g[j].z, u[j].z); upd(w[j].w, g[j].w, u[j].w);
         w4[i + j * nth] = w[j];
-        u4[i + j * nth] = u[j];
-        if (write_back_grad) g4[i + j * nth] = g[j];
+        __stcs(u4 + i + j * nth, u[j]);
+        if (write_back_grad) __stcs(g4 + i + j * nth, g[j]);
       }
     }
     for (; i < n4; i += nth) {
@@ -142,15 +151,29 @@ extern "C" int b200_sgd_multi_tensor_ex(b200_ctx *ctx, int ntensors, const b200_
   if (ntensors <= 0) return B200_OK;
   size_t max_n = 0;
   for (int i = 0; i < ntensors; ++i) max_n = tensors_host[i].n > max_n ? (size_t)tensors_host[i].n : max_n;
-  size_t blocks_x = (max_n / 4 + (size_t)TPB * UNROLL - 1) / ((size_t)TPB * UNROLL);
-  // persistent-ish: cap at 8 CTAs per SM worth of blocks over all tensors
-  size_t cap = (size_t)ctx->sm_count * 8;
-  if (blocks_x > cap) blocks_x = cap;
-  if (blocks_x < 1) blocks_x = 1;
-  dim3 grid((unsigned)blocks_x, (unsigned)ntensors);
-  PREFER_MAX_SMEM_ONCE(sgd_kernel);
-  sgd_kernel<<<grid, TPB, 0, ctx->stream>>>(tensors_dev, decay, count_dev, flags);
-  LAUNCH_CHECK(ctx);
+  if (ntensors == 1 && max_n >= (1u << 20)) {
+    // one big tensor: one 1024-thread CTA per SM, grid-stride inside (1024 x 12 x 16 B in flight per SM)
+    static bool attr = false;
+    if (!attr) {
+      CUDA_TRY(cudaFuncSetAttribute(sgd_kernel<TPB_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, SGD_BIG_SMEM));
+      attr = true;
+    }
+    const int sms = ctx->sm_budget > 0 ? ctx->sm_budget : ctx->sm_count;
+    size_t blocks = (max_n / 4 + (size_t)TPB_BIG * UNROLL - 1) / ((size_t)TPB_BIG * UNROLL);
+    if (blocks > (size_t)sms) blocks = (size_t)sms;
+    sgd_kernel<TPB_BIG><<<dim3((unsigned)blocks, 1), TPB_BIG, SGD_BIG_SMEM, ctx->stream>>>(tensors_dev, decay, count_dev, flags);
+    LAUNCH_CHECK(ctx);
+  } else {
+    size_t blocks_x = (max_n / 4 + (size_t)TPB * UNROLL - 1) / ((size_t)TPB * UNROLL);
+    // persistent-ish: cap at 4 CTAs per SM worth of blocks per tensor
+    size_t cap = (size_t)ctx->sm_count * 4;
+    if (blocks_x > cap) blocks_x = cap;
+    if (blocks_x < 1) blocks_x = 1;
+    dim3 grid((unsigned)blocks_x, (unsigned)ntensors);
+    PREFER_MAX_SMEM_ONCE(sgd_kernel<TPB>);
+    sgd_kernel<TPB><<<grid, TPB, 0, ctx->stream>>>(tensors_dev, decay, count_dev, flags);
+    LAUNCH_CHECK(ctx);
+  }
   for (int i = 0; i < ntensors; ++i) {
     const b200_sgd_tensor &t = tensors_host[i];
     if (t.max_norm_penalty > 0.0f) {

@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(256) skinny_fwd_ksplit_kernel(int M, int N, in
 // multiclass_cross_entropy_loss_function.cc:61-71) and the data gradient of its rows need nothing from
 // other CTAs.
 template <int NT, int R>
-__global__ void __launch_bounds__(256) output_layer_fused_kernel(int M, int N, int K, const float *__restrict__ X, int ldx,
+__global__ void __launch_bounds__(256, (R <= 4) ? 2 : 1) output_layer_fused_kernel(int M, int N, int K, const float *__restrict__ X, int ldx,
                                                                  const float *__restrict__ W, int ldw,
                                                                  const float *__restrict__ bias,
                                                                  const float *__restrict__ target, float *__restrict__ logits,
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(256) output_layer_fused_kernel(int M, int N, i
                                                                  float *__restrict__ grad, int dact, float *__restrict__ dX,
                                                                  int lddx) {
   constexpr int V = R * NT;
-  static_assert(V % 32 == 0 && R == 8, "8 rows per CTA");
+  static_assert(V % 32 == 0 && R <= 8, "R*NT must be a multiple of 32");
   __shared__ float red[8][V];
   __shared__ float sg[R][NT];          // logits, then the gradient rows
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -261,6 +261,8 @@ __global__ void __launch_bounds__(256) output_layer_fused_kernel(int M, int N, i
   // only the stores are predicated.
 #pragma unroll 1
   for (int k = w * 128 + lane * 4; k < K; k += 8 * 128) {
+    // every load of the iteration is issued before the first use (a load consumed right after its issue
+    // serialises the L2 round trips: 25 us instead of 9 for the whole kernel)
     float4 wv[NT], y[R];
 #pragma unroll
     for (int n = 0; n < NT; ++n) wv[n] = ldg4(W + (size_t)min(n, N - 1) * ldw + k);
@@ -636,6 +638,8 @@ extern "C" int b200_output_layer_fused(b200_ctx *ctx, int M, int N, int K, const
     b200_set_error("b200_output_layer_fused: needs N <= %d, K %% 4 == 0 and 16-byte aligned rows", SK_MAXN);
     return B200_ERR_UNSUPPORTED;
   }
+  // 8 rows per CTA, one CTA per SM (4 rows per CTA with two CTAs per SM measured 14 us against 9 us: the
+  // class padding to 16 and the second read of W cost more than the extra warps hide)
   constexpr int R = 8;
   const int grid = (M + R - 1) / R;
   NT_DISPATCH(N, {
