@@ -446,22 +446,35 @@ void SupervisedTrainer::runStep(const MatrixPtr &x, const MatrixPtr &t, int glob
       if (i >= 0) done[i] = 1;
       flush(false);
     };
+    // same branch structure as the single-replica step: weight gradients on side branches (the all-reduce
+    // of a bucket waits for every branch that may hold part of it), statistics on branch 0
+    net->use_branches = use_branches;
+    if (use_branches) check(b200_branch_begin(ctx, 0));
+    loss.accumLoss(rows);
+    if (use_branches) check(b200_branch_end(ctx));
     try {
       net->doBackprop(grad);
+      cleanup();
+      for (int i = 0; i < nt; ++i) done[i] = 1;   // tensors no component touched this step stay zero: reduce them too
+      flush(true);
+      // every bucket but the last is updated on branch 0 as soon as it has arrived, beside the contractions
+      // still running; the last one on the main stream after the join, and it bumps the step counter
+      for (size_t b = 0; b < buckets.size(); ++b) {
+        const bool last = (b + 1 == buckets.size());
+        if (last) check(b200_branch_join_all(ctx));
+        else if (use_branches) check(b200_branch_begin(ctx, 0));
+        check(b200_comm_wait(ctx, (int)b));
+        check(b200_sgd_multi_tensor_ex(ctx, buckets[b].second - buckets[b].first, sgd_dev + buckets[b].first,
+                                       sgd_host.data() + buckets[b].first, decay, count_dev,
+                                       wb | (last ? B200_SGD_INCREMENT_COUNT : 0)));
+        if (!last && use_branches) check(b200_branch_end(ctx));
+      }
+      if (buckets.empty()) check(b200_branch_join_all(ctx));
     } catch (...) {
       cleanup();
+      b200_branch_join_all(ctx);
       throw;
     }
-    cleanup();
-    for (int i = 0; i < nt; ++i) done[i] = 1;   // tensors no component touched this step stay zero: reduce them too
-    flush(true);
-    for (size_t b = 0; b < buckets.size(); ++b) {
-      check(b200_comm_wait(ctx, (int)b));
-      const int last = (b + 1 == buckets.size()) ? B200_SGD_INCREMENT_COUNT : 0;
-      check(b200_sgd_multi_tensor_ex(ctx, buckets[b].second - buckets[b].first, sgd_dev + buckets[b].first,
-                                     sgd_host.data() + buckets[b].first, decay, count_dev, wb | last));
-    }
-    loss.accumLoss(rows);
   } else {
     // Single replica: the loss statistics, the weight gradients and the updates run on side branches;
     // only the data gradients stay on the critical path.  The tensor of a big contraction is updated by

