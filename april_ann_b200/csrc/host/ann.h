@@ -350,6 +350,16 @@ class SupervisedTrainer {
   // data-parallel replica group (weights identical on every rank; gradients summed)
   void setDataParallel(int nranks, int rank) { dp_nranks = nranks; dp_rank = rank; }
   void broadcastWeights();
+  // replica group over NVLink peer memory (b200_dp_fused_update): dpExport writes the CUDA IPC handles of
+  // this rank's weight arena, gradient arena and flag block (3 x 64 bytes); dpConnect maps every peer's
+  void dpExport(int nranks, unsigned char *handles256);
+  void dpConnect(int nranks, int rank, const unsigned char *all_handles);
+  float dpBench(int reps);
+  bool dp_fused = false;
+  b200_dp_group dp_group = {};
+  long long *dp_flags = nullptr;
+  float *dp_recv = nullptr;
+  std::vector<void *> dp_imported;
 
   b200_ctx *ctx;
   std::shared_ptr<StackANNComponent> net;

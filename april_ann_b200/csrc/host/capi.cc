@@ -252,5 +252,19 @@ int b200h_trainer_set_data_parallel(b200_trainer *t, int nranks, int rank) {
   API_TRY(t->t->setDataParallel(nranks, rank))
 }
 int b200h_trainer_broadcast_weights(b200_trainer *t) { API_TRY(t->t->broadcastWeights()) }
+int b200h_trainer_dp_bench(b200_trainer *t, int reps, float *us_per_update) { API_TRY(*us_per_update = t->t->dpBench(reps)) }
+int b200h_trainer_dp_debug(b200_trainer *t, long long *stamps64) {
+  API_TRY(
+      if (!t->t->dp_flags) throw b200::Error(B200_ERR_BAD_ARG, "no replica group");
+      b200::check(b200_sync(t->t->ctx));
+      b200::check(b200_memcpy_d2h(t->t->ctx, stamps64, (char *)t->t->dp_flags + b200_dp_debug_offset(), 64 * sizeof(long long)));
+      b200::check(b200_sync(t->t->ctx)))
+}
+int b200h_trainer_dp_export(b200_trainer *t, int nranks, void *handles256) {
+  API_TRY(t->t->dpExport(nranks, (unsigned char *)handles256))
+}
+int b200h_trainer_dp_connect(b200_trainer *t, int nranks, int rank, const void *all_handles) {
+  API_TRY(t->t->dpConnect(nranks, rank, (const unsigned char *)all_handles))
+}
 
 }  // extern "C"

@@ -166,6 +166,9 @@ SupervisedTrainer::~SupervisedTrainer() {
   if (count_dev) b200_free(ctx, count_dev);
   if (sgd_dev) b200_free(ctx, sgd_dev);
   if (sgd_light_dev) b200_free(ctx, sgd_light_dev);
+  for (void *p : dp_imported) b200_ipc_close(ctx, p);
+  if (dp_flags) b200_free(ctx, dp_flags);
+  if (dp_recv) b200_free(ctx, dp_recv);
 }
 
 void SupervisedTrainer::build(unsigned input, unsigned output) {
@@ -421,7 +424,65 @@ void SupervisedTrainer::runStep(const MatrixPtr &x, const MatrixPtr &t, int glob
     net->use_branches = false;
     net->last_actf_backprop_is_identity = false;
   };
-  if (dp_nranks > 1) {
+  bool any_max_norm = false;
+  for (auto &t : sgd_host) any_max_norm = any_max_norm || t.max_norm_penalty > 0.0f;
+  if (dp_nranks > 1 && dp_fused && !keep_gradients && !any_max_norm) {
+    // Replica group over NVLink peer memory: one kernel per bucket reduces the peers' gradient shards, updates
+    // this rank's shard and writes the new weights into every replica (b200_dp_fused_update).  A bucket is
+    // launched once its gradients are final AND the data gradients that read its weights have been issued
+    // (the peers will overwrite them), on branch 0 beside the contractions still to come; the last bucket
+    // on the main stream after the join.  b200_dp_wait then holds the step until every shard has landed.
+    int next = 0, nbuckets = 0;
+    auto launchBucket = [&](int lo, int hi, bool last) {
+      if (last) {
+        check(b200_branch_join_all(ctx));
+      } else if (use_branches) {
+        check(b200_branch_begin(ctx, 0));
+        check(b200_branch_wait(ctx, 1));
+        check(b200_branch_wait(ctx, 2));
+        int sms = 0;
+        check(b200_sm_count(ctx, &sms));
+        check(b200_set_sm_budget(ctx, sms - sms / 2));
+      }
+      check(b200_dp_fused_update(ctx, &dp_group, hi - lo, sgd_dev + lo, sgd_host.data() + lo, decay, count_dev, nbuckets));
+      check(b200_set_sm_budget(ctx, 0));
+      if (!last && use_branches) check(b200_branch_end(ctx));
+      ++nbuckets;
+    };
+    auto flush = [&](bool force) {
+      int hi = next;
+      size_t bytes = 0;
+      while (hi < nt && done[hi]) { bytes += grads[arena_order[hi]]->size() * sizeof(float); ++hi; }
+      if (hi == next) return;
+      if (!force && bytes < dp_bucket_bytes && hi < nt) return;
+      if (nbuckets >= 15 && hi < nt) return;   // keep one slot for the tail
+      launchBucket(next, hi, force || hi == nt);
+      next = hi;
+    };
+    net->use_branches = use_branches;
+    net->on_backprop_issued = [&](ANNComponent *c, int) {
+      if (!isFinalContribution(c)) return;
+      const int i = tensorIndex(c->getWeightsName());
+      if (i >= 0) done[i] = 1;
+      flush(false);
+    };
+    if (use_branches) check(b200_branch_begin(ctx, 0));
+    loss.accumLoss(rows);
+    if (use_branches) check(b200_branch_end(ctx));
+    try {
+      net->doBackprop(grad);
+      cleanup();
+      for (int i = 0; i < nt; ++i) done[i] = 1;   // tensors no component touched this step: zero gradient on every rank
+      flush(true);
+      check(b200_branch_join_all(ctx));
+      check(b200_dp_wait(ctx, &dp_group, nbuckets, count_dev));
+      check(b200_counter_increment(ctx, count_dev));
+    } catch (...) {
+      cleanup();
+      b200_branch_join_all(ctx);
+      throw;
+    }
+  } else if (dp_nranks > 1) {
     // Replica group: finished gradients are all-reduced bucket by bucket on the communication stream
     // while the rest of the backward pass runs, and each bucket is updated as soon as it has arrived.
     std::vector<std::pair<int, int>> buckets;   // [first, last) tensor indices in arena order
@@ -742,6 +803,82 @@ double SupervisedTrainer::norm2(const std::string &pattern) {
     }
   }
   return best;
+}
+
+void SupervisedTrainer::dpExport(int nranks, unsigned char *handles) {
+  if (weights_order.empty()) throw Error(B200_ERR_NOT_BUILT, "Execute build method before joining a replica group");
+  if (nranks < 2 || nranks > B200_DP_MAX_RANKS) throw Error(B200_ERR_BAD_ARG, "replica group of 2..8 ranks");
+  if (!dp_flags) {
+    void *p;
+    check(b200_malloc(ctx, &p, b200_dp_flags_bytes()));
+    dp_flags = (long long *)p;
+    check(b200_memset_zero(ctx, dp_flags, b200_dp_flags_bytes()));
+    // receive block: one arena-shaped slot per peer (only this rank's shards of it are ever written)
+    const size_t bytes = (size_t)(nranks - 1) * weights_arena->size() * sizeof(float);
+    check(b200_malloc(ctx, &p, bytes));
+    dp_recv = (float *)p;
+    check(b200_memset_zero(ctx, dp_recv, bytes));
+    check(b200_sync(ctx));
+  }
+  check(b200_ipc_export(ctx, weights_arena->data, handles));
+  check(b200_ipc_export(ctx, grads_arena->data, handles + 64));
+  check(b200_ipc_export(ctx, dp_flags, handles + 128));
+  check(b200_ipc_export(ctx, dp_recv, handles + 192));
+}
+void SupervisedTrainer::dpConnect(int nranks, int rank, const unsigned char *all) {
+  if (nranks < 2 || nranks > B200_DP_MAX_RANKS) throw Error(B200_ERR_BAD_ARG, "replica group of 2..8 ranks");
+  if (!dp_flags) throw Error(B200_ERR_BAD_ARG, "dpExport first");
+  dp_group = b200_dp_group{};
+  dp_group.nranks = nranks;
+  dp_group.rank = rank;
+  dp_group.arena_elems = weights_arena->size();
+  for (int p = 0; p < nranks; ++p) {
+    if (p == rank) {
+      dp_group.weights[p] = weights_arena->data;
+      dp_group.grads[p] = grads_arena->data;
+      dp_group.flags[p] = dp_flags;
+      dp_group.recv[p] = dp_recv;
+      continue;
+    }
+    void *ptr[4] = {nullptr, nullptr, nullptr, nullptr};
+    for (int k = 0; k < 4; ++k) {
+      check(b200_ipc_import(ctx, all + (size_t)p * 256 + 64 * k, &ptr[k]));
+      dp_imported.push_back(ptr[k]);
+    }
+    dp_group.weights[p] = (float *)ptr[0];
+    dp_group.grads[p] = (float *)ptr[1];
+    dp_group.flags[p] = (long long *)ptr[2];
+    dp_group.recv[p] = (float *)ptr[3];
+  }
+  dp_fused = true;
+  if (const char *e = getenv("B200_DP_FUSED")) dp_fused = atoi(e) != 0;
+  for (auto &kv : graphs) delete kv.second;
+  graphs.clear();
+}
+
+float SupervisedTrainer::dpBench(int reps) {
+  if (!dp_fused) throw Error(B200_ERR_BAD_ARG, "dpConnect first");
+  if (sgd_dirty) uploadSgdTable();
+  const double decay = optimizer.getOption("decay");
+  cudaEvent_t e0, e1;
+  cudaCheck(cudaEventCreate(&e0), "cudaEventCreate");
+  cudaCheck(cudaEventCreate(&e1), "cudaEventCreate");
+  cudaStream_t stream = (cudaStream_t)b200_stream(ctx);
+  auto once = [&]() {
+    check(b200_dp_fused_update(ctx, &dp_group, (int)sgd_host.size(), sgd_dev, sgd_host.data(), decay, count_dev, 0));
+    check(b200_dp_wait(ctx, &dp_group, 1, count_dev));
+    check(b200_counter_increment(ctx, count_dev));
+  };
+  for (int i = 0; i < 3; ++i) once();
+  cudaCheck(cudaEventRecord(e0, stream), "cudaEventRecord");
+  for (int i = 0; i < reps; ++i) once();
+  cudaCheck(cudaEventRecord(e1, stream), "cudaEventRecord");
+  cudaCheck(cudaEventSynchronize(e1), "cudaEventSynchronize");
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return ms * 1e3f / (float)reps;
 }
 
 void SupervisedTrainer::broadcastWeights() {

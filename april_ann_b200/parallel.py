@@ -37,7 +37,7 @@ def exchange_unique_id(dist):
     return obj[0]
 
 
-def init_data_parallel(trainer, dist):
+def init_data_parallel(trainer, dist, fused=True):
     """Creates the NCCL communicator of the trainer's context, makes the trainer scale gradients
     by the global bunch and all-reduce them, and broadcasts rank 0's weights to every replica."""
     world, rank = dist.get_world_size(), dist.get_rank()
@@ -46,3 +46,35 @@ def init_data_parallel(trainer, dist):
     trainer.set_data_parallel(world, rank)
     trainer.broadcast_weights()
     dist.barrier()
+    if fused and 2 <= world <= 8:
+        connect_peer_memory(trainer, dist)
+    dist.barrier()
+
+
+def connect_peer_memory(trainer, dist):
+    """Maps every rank's weight arena, gradient arena and flag block into this process (CUDA IPC; the
+    64-byte handles travel over the host-side rendezvous) so that the update of a step runs as one
+    reduce-scatter + SGD + all-gather kernel over NVLink (csrc/dp_fused.cu).  Every rank must succeed,
+    otherwise all of them stay on the NCCL all-reduce path."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    mine = (C.c_ubyte * 256)()
+    ok = True
+    try:
+        check(lib.b200h_trainer_dp_export(trainer.h, C.c_int(world), mine))
+    except Exception:
+        ok = False
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (ok, bytes(mine)))
+    if not all(g[0] for g in gathered):
+        return False
+    blob = b"".join(g[1] for g in gathered)
+    buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+    try:
+        check(lib.b200h_trainer_dp_connect(trainer.h, C.c_int(world), C.c_int(rank), buf))
+    except Exception:
+        ok = False
+    flags = [None] * world
+    dist.all_gather_object(flags, ok)
+    if not all(flags):
+        raise RuntimeError("peer-memory replica group: some ranks could not map their peers (set fused=False)")
+    return True

@@ -210,9 +210,9 @@ int b200_counter_increment(b200_ctx *ctx, int64_t *count_dev);
 
 /* ------------------------------------------------------------------ replica group over NVLink peer memory
  * New relative to the reference (single device, gpu_helper.h:65-68).  b200_dp_fused_update is the
- * data-parallel update as one kernel: gradient reduce-scatter (P2P loads of the peers' gradient shards),
- * the SGD step above on the rank's shard, all-gather of the updated weights (P2P stores into every
- * replica).  The arenas of every rank are mapped into each process with CUDA IPC
+ * data-parallel update as one kernel: gradient reduce-scatter (every rank pushes its gradients of the
+ * peers' shards into their receive blocks with P2P stores), the SGD step above on the rank's shard,
+ * all-gather of the updated weights (P2P stores into every replica).  The arenas of every rank are mapped into each process with CUDA IPC
  * (b200_ipc_export / _import: the 64-byte handle travels over the host-side rendezvous).  Ordering
  * between GPUs: per (bucket, rank) step tags in `flags` (b200_dp_flags_bytes() bytes per rank, zeroed
  * once); b200_dp_wait, at the end of a step, returns once every rank's shard of every bucket has landed. */
@@ -220,13 +220,17 @@ int b200_counter_increment(b200_ctx *ctx, int64_t *count_dev);
 typedef struct {
   float *grads[B200_DP_MAX_RANKS];      /* base of every rank's gradient arena (own entry = local pointer) */
   float *weights[B200_DP_MAX_RANKS];    /* base of every rank's weight arena */
+  float *recv[B200_DP_MAX_RANKS];       /* every rank's receive block: (nranks-1) x arena_elems floats, one arena-shaped
+                                           slot per source rank (sources in rank order, the owner skipped) */
   long long *flags[B200_DP_MAX_RANKS];  /* every rank's flag block */
+  uint64_t arena_elems;                 /* floats of one arena (same on every rank) */
   int32_t nranks, rank;
 } b200_dp_group;
 int b200_ipc_export(b200_ctx *ctx, void *dptr, void *handle64);
 int b200_ipc_import(b200_ctx *ctx, const void *handle64, void **dptr);
 int b200_ipc_close(b200_ctx *ctx, void *dptr);
 size_t b200_dp_flags_bytes(void);
+size_t b200_dp_debug_offset(void);   /* bring-up: 4 globaltimer stamps per bucket live behind the tags */
 int b200_dp_fused_update(b200_ctx *ctx, const b200_dp_group *grp, int ntensors, const b200_sgd_tensor *tensors_dev,
                          const b200_sgd_tensor *tensors_host, double decay, int64_t *count_dev, int bucket);
 int b200_dp_wait(b200_ctx *ctx, const b200_dp_group *grp, int nbuckets, const int64_t *count_dev);

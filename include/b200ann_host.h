@@ -101,6 +101,17 @@ int b200h_trainer_last_loss_async(b200_trainer *t, double *pinned_out);  /* enqu
 /* data parallel replica group */
 int b200h_trainer_set_data_parallel(b200_trainer *t, int nranks, int rank);
 int b200h_trainer_broadcast_weights(b200_trainer *t);
+/* replica group over NVLink peer memory: export this rank's 4 CUDA IPC handles (weights arena, gradient
+ * arena, flag block, receive block: 256 bytes), exchange them over the host-side rendezvous, connect with
+ * everybody's (nranks x 256 bytes, rank order).  Afterwards train steps use b200_dp_fused_update instead
+ * of NCCL. */
+int b200h_trainer_dp_export(b200_trainer *t, int nranks, void *handles256);
+/* measurement hook (tools/dp_bench.py): `reps` fused updates over ALL parameters back to back, every rank
+ * in step; returns the mean time of one (CUDA events).  Weights are advanced with whatever the gradient
+ * arenas hold. */
+int b200h_trainer_dp_bench(b200_trainer *t, int reps, float *us_per_update);
+int b200h_trainer_dp_debug(b200_trainer *t, long long *stamps64);   /* 4 globaltimer stamps per bucket of the last step */
+int b200h_trainer_dp_connect(b200_trainer *t, int nranks, int rank, const void *all_handles);
 
 #ifdef __cplusplus
 }

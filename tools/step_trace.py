@@ -56,6 +56,14 @@ with profile(activities=[ProfilerActivity.CUDA]) as prof:
     ctx.sync()
 path = os.path.join(tempfile.mkdtemp(), "trace.json")
 prof.export_chrome_trace(path)
+if world > 1:
+    import ctypes as C
+    from april_ann_b200._lib import lib, check
+    st = (C.c_longlong * 64)()
+    check(lib.b200h_trainer_dp_debug(tr.h, st))
+    for b in range(2):
+        print("rank %d bucket %d: start %d ns after bucket 0 start; wait for peers %d, shard update %d, publish %d ns" % (
+            rank, b, st[4 * b] - st[0], st[4 * b + 1] - st[4 * b], st[4 * b + 2] - st[4 * b + 1], st[4 * b + 3] - st[4 * b + 2]), flush=True)
 if rank != 0:
     sys.exit(0)
 ev = [e for e in json.load(open(path))["traceEvents"] if e.get("cat") == "kernel"]
