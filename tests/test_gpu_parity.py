@@ -556,3 +556,50 @@ def test_tf32_fused_layer_passes(ann, ops, act):
     assert rel_l2(dx, want_dx) < TF32_TOL
     assert rel_l2(dw, dW0 + (dY.T @ X) / 32) < TF32_TOL
     assert rel_l2(db, dY.sum(axis=0) / 32) < F32_TOL * 10
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,N,K", [(333, 512, 200), (4096, 256, 4096), (1024, 2048, 2048), (130, 64, 33 * 4)])
+def test_tf32_relu_data_gradient_mask_edges(ann, ops, M, N, K):
+    """dX = (dY . W) (.) relu'(Y_below) on the tensor cores: the derivative arrives as bit masks gathered
+    while the contraction runs.  Ragged rows / columns, a split-K shape, and a persistent multi-tile shape
+    (earlier tiles of a CTA take the one-warp-per-quadrant path with eight masks per warp)."""
+    ctx = ann.get_context()
+    dY, W = rnd_mat(90, M, N), rnd_mat(91, N, K, lo=-0.05, hi=0.05)
+    Y = A.relu(rnd_mat(92, M, K, lo=-1, hi=1))
+    ctx.set_math_mode(ann.MATH_TF32)
+    try:
+        dx = ops.linear_bwd_data(dY, W, "relu", Y)
+    finally:
+        ctx.set_math_mode(ann.MATH_FP32)
+    want = A.relu_der(Y) * (dY.astype(np.float64) @ W.astype(np.float64)).astype(np.float32)
+    assert rel_l2(dx, want) < TF32_TOL
+    assert np.array_equal(dx == 0, (want == 0) | (dx == 0))      # nothing leaks through a closed gate
+    assert not np.any((Y <= 0) & (dx != 0))
+
+
+@pytest.mark.gpu
+def test_pipelined_feed_equals_train_step(ann):
+    """stage() / step_staged() (two staging slots filled on a copy stream, one captured graph per slot)
+    must give exactly the weights and the loss statistics of train_step() on the same bunches."""
+    topo = "64 inputs 48 relu 32 tanh 10 log_softmax"
+
+    def make():
+        tr = ann.trainable.supervised_trainer(ann.mlp.all_all.generate(topo), ann.loss.multi_class_cross_entropy(), 32).build()
+        tr.set_option("learning_rate", 0.05)
+        tr.set_option("momentum", 0.8)
+        tr.set_option("weight_decay", 1e-3)
+        tr.randomize_weights(random=ann.random(77), inf=-1, sup=1, use_fanin=True, use_fanout=True)
+        return tr
+    a, b = make(), make()
+    xs = [rnd_mat(100 + k, 32, 64) for k in range(9)]
+    ts = [onehot(200 + k, 32, 10) for k in range(9)]
+    la = [a.train_step(x, t)[0] for x, t in zip(xs, ts)]
+    b.loss_reset()
+    for x, t in zip(xs, ts):
+        b.stage(x, t, 32)
+        b.step_staged(32)
+    mean_b, _ = b.loss_get()
+    assert abs(mean_b - float(np.mean(la))) < 1e-5
+    for n in a.weight_names():
+        assert np.array_equal(a.weights(n), b.weights(n)), n
