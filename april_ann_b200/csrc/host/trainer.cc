@@ -546,6 +546,7 @@ void SupervisedTrainer::runStep(const MatrixPtr &x, const MatrixPtr &t, int glob
     if (use_branches) check(b200_branch_begin(ctx, 0));
     loss.accumLoss(rows);
     if (use_branches) check(b200_branch_end(ctx));
+    int last_heavy = -1;
     ANNComponent *first_heavy = nullptr;   // its tensor is the last one of the backward pass
     for (auto *c : net->flatComponents()) {
       if (!c->hasWeightsName()) continue;
@@ -557,6 +558,12 @@ void SupervisedTrainer::runStep(const MatrixPtr &x, const MatrixPtr &t, int glob
       if (!isFinalContribution(c)) return;
       const int i = tensorIndex(c->getWeightsName());
       if (i < 0 || done[i] || !tensor_heavy[i] || !sgd_as_ready) return;
+      if (c == first_heavy) {
+        // the last tensor of the backward pass: updated on the main stream after the join (below), where its
+        // launch can also bump the step counter
+        last_heavy = i;
+        return;
+      }
       if (use_branches) {
         const int b = (c == first_heavy && branch > 0) ? branch : 0;
         check(b200_branch_begin(ctx, b));
@@ -583,7 +590,7 @@ void SupervisedTrainer::runStep(const MatrixPtr &x, const MatrixPtr &t, int glob
         check(b200_sgd_multi_tensor_ex(ctx, nt, sgd_dev, sgd_host.data(), decay, count_dev, wb | B200_SGD_INCREMENT_COUNT));
       }
       for (int i = 0; i < nt && sgd_as_ready; ++i) {
-        if (done[i] || !tensor_heavy[i]) continue;
+        if (done[i] || !tensor_heavy[i] || i == last_heavy) continue;
         check(b200_sgd_multi_tensor_ex(ctx, 1, sgd_dev + i, sgd_host.data() + i, decay, count_dev, wb));
         done[i] = 1;
       }
@@ -594,8 +601,17 @@ void SupervisedTrainer::runStep(const MatrixPtr &x, const MatrixPtr &t, int glob
         if (use_branches) check(b200_branch_end(ctx));
       }
       check(b200_branch_join_all(ctx));
-      // the updates ran on several streams: bump the counter once they are joined
-      if (sgd_as_ready) check(b200_counter_increment(ctx, count_dev));
+      // the updates ran on several streams: the counter is bumped once they are joined -- by the last big
+      // tensor's update (its last CTA to finish does it) when there is one, else by a launch of its own
+      if (sgd_as_ready) {
+        if (last_heavy >= 0) {
+          check(b200_sgd_multi_tensor_ex(ctx, 1, sgd_dev + last_heavy, sgd_host.data() + last_heavy, decay, count_dev,
+                                         wb | B200_SGD_INCREMENT_COUNT));
+          done[last_heavy] = 1;
+        } else {
+          check(b200_counter_increment(ctx, count_dev));
+        }
+      }
     } catch (...) {
       cleanup();
       b200_branch_join_all(ctx);
