@@ -176,6 +176,7 @@ struct TcParams {
   int BN;            // N tile (multiple of 16, <= 256)
   int stages;        // smem ring depth (<= MAX_STAGES)
   uint32_t stage_bytes;   // A_BYTES + B tile bytes (multiple of 1 KiB)
+  uint32_t staging_bytes; // dedicated store staging: 16 KiB (one 4 KiB tile per quadrant) or 32 KiB (one per epilogue warp)
   int ldc;
   float *C;
   GemmEpilogue ep;
@@ -405,7 +406,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int STAGES = p.stages;
   const uint32_t STAGE_BYTES = p.stage_bytes;
   const uint32_t staging = smem_base + STAGES * STAGE_BYTES;
-  const uint32_t bars = staging + STAGING_BYTES;
+  const uint32_t bars = staging + p.staging_bytes;
   // barrier layout (8 bytes each): full[8] empty[8] tmem_full[2] tmem_empty[2] ; then the TMEM base slot
   auto full_bar = [&](int s) { return bars + 8 * s; };
   auto empty_bar = [&](int s) { return bars + 8 * (MAX_STAGES + s); };
@@ -576,7 +577,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           lo = crank ? own0 : 0;
           hi = crank ? nch_p : own0;
         }
-        if (tile + tile_step >= num_tiles) {
+        if (tile + tile_step >= num_tiles || p.staging_bytes >= (uint32_t)(EPI_WARPS * 4096)) {
           const int mid = lo + ((hi - lo + 1) >> 1);
           if (half) lo = mid; else hi = mid;
         } else if (half) {
@@ -682,6 +683,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           stg.base = staging + (uint32_t)quad * 4096u;
           stg.nbuf = 1;
         }
+      } else if (p.staging_bytes >= (uint32_t)(EPI_WARPS * 4096)) {
+        // the ring is busy with the next tile; launches with more tiles than CTAs carry a dedicated 4 KiB tile
+        // per epilogue warp, so all eight warps work (short-K shapes are epilogue bound otherwise)
+        const int ch_mid = ch_lo + ((ch_hi - ch_lo + 1) >> 1);
+        w_lo = half ? ch_mid : ch_lo;
+        w_hi = half ? ch_hi : ch_mid;
+        stg.base = staging + (uint32_t)ew * 4096u;
+        stg.stride = 0;
+        stg.nbuf = 1;
       } else {
         // the ring is busy with the next tile: one warp per quadrant, dedicated buffer
         w_lo = half ? ch_hi : ch_lo;
@@ -878,7 +888,7 @@ int launch(b200_ctx *ctx, TcState *s, int idx, const CUtensorMap &ma, const CUte
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
     s->attr_set[idx] = true;
   }
-  const size_t smem = (size_t)p.stages * p.stage_bytes + SMEM_EXTRA;
+  const size_t smem = (size_t)p.stages * p.stage_bytes + SMEM_EXTRA - STAGING_BYTES + p.staging_bytes;
   if (p.splitk == 2) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
@@ -953,7 +963,16 @@ int gemm_tc(b200_ctx *ctx, int transA, int transB, int M, int N, int K, const fl
   }
   // the ring is as deep as shared memory allows: loads are latency/bandwidth bound, so bytes in flight matter
   p.stage_bytes = (uint32_t)A_BYTES + (b_k ? (uint32_t)p.BN * BK * 4 : (uint32_t)((p.BN + 31) / 32) * 4096u);
-  p.stages = (SMEM_BUDGET - SMEM_EXTRA) / (int)p.stage_bytes;
+  {
+    // launches with more tiles than CTAs (persistent CTAs, the epilogue of a tile runs under the next main loop)
+    // fill the device by themselves: they take the whole shared memory and a staging tile per epilogue warp;
+    // single-tile launches stay under SMEM_BUDGET so that light kernels can be resident beside them
+    const long tiles_all = (long)((M + BM - 1) / BM) * ((N + p.BN - 1) / p.BN);
+    const bool multi = p.splitk != 2 && tiles_all > sms;
+    p.staging_bytes = multi ? (uint32_t)(EPI_WARPS * 4096) : (uint32_t)STAGING_BYTES;
+    const int budget = multi ? SMEM_MAX : SMEM_BUDGET;
+    p.stages = (budget - (SMEM_EXTRA - STAGING_BYTES + (int)p.staging_bytes)) / (int)p.stage_bytes;
+  }
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
   if (s->force_stages > 0 && s->force_stages < p.stages) p.stages = s->force_stages;
   p.ldc = ldc;

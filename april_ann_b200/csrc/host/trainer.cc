@@ -574,7 +574,8 @@ void SupervisedTrainer::runStep(const MatrixPtr &x, const MatrixPtr &t, int glob
       if (use_branches && c != first_heavy && net->contraction_mode == 1) {
         int sms = 0;
         check(b200_sm_count(ctx, &sms));
-        check(b200_set_sm_budget(ctx, sms - sms / 2));
+        const long tiles = (long)((sgd_host[i].rows + 127) / 128) * (long)((sgd_host[i].cols + 255) / 256);
+        if (tiles <= sms) check(b200_set_sm_budget(ctx, sms - sms / 2));   // same small-layer regime as the contractions
       }
       check(b200_sgd_multi_tensor_ex(ctx, 1, sgd_dev + i, sgd_host.data() + i, decay, count_dev, wb));
       check(b200_set_sm_budget(ctx, 0));
