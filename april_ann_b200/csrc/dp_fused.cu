@@ -177,19 +177,23 @@ dp_fused_update_kernel(const b200_dp_group grp, const b200_sgd_tensor *__restric
         if (p < nranks && (p == rank || !(dbg & 2))) *(reinterpret_cast<float4 *>(grp.weights[p]) + el[j]) = w[j];
     }
   }
-  // ---- this rank's shard is in every replica: publish
+  // ---- this rank's shard is in every replica: publish.  The last CTA to get here tells every peer, one
+  //      thread per peer (a single thread doing nranks release stores to remote GPUs pays each round trip in turn)
+  __shared__ int s_last;
   __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
     unsigned long long *ticket = ticket_slot(grp.flags[rank], 1);
-    const bool last = atomicAdd(ticket, 1ull) == (unsigned long long)gridDim.x - 1;
-    if (last) {
+    s_last = atomicAdd(ticket, 1ull) == (unsigned long long)gridDim.x - 1;
+    if (s_last) {
       *ticket = 0ull;
       *dbg_slot(grp.flags[rank], bucket, 2) = gtime();
-      __threadfence_system();
-      for (int p = 0; p < nranks; ++p) st_release_sys(done_slot(grp.flags[p], bucket, rank), tag);
-      *dbg_slot(grp.flags[rank], bucket, 3) = gtime();
     }
+  }
+  __syncthreads();
+  if (s_last) {
+    if (threadIdx.x < nranks) st_release_sys(done_slot(grp.flags[threadIdx.x], bucket, rank), tag);
+    if (threadIdx.x == 0) *dbg_slot(grp.flags[rank], bucket, 3) = gtime();
   }
 }
 
