@@ -141,6 +141,12 @@ int b200h_trainer_set_flag(b200_trainer *t, const char *flag, int value) {
     std::string f = str(flag);
     if (f == "fuse") t->net->fuse = value != 0;
     else if (f == "cuda_graph") t->t->use_cuda_graph = value != 0;
+    else if (f == "branches") t->t->use_branches = value != 0;
+    else if (f == "fuse_output_layer") t->t->fuse_output_layer = value != 0;
+    else if (f == "dp_fused") {   // 0: back to the NCCL all-reduce path (1 needs a connected replica group)
+      if (value != 0 && t->t->dp_group.nranks < 2) throw Error(B200_ERR_BAD_ARG, "dp_fused needs b200h_trainer_dp_connect");
+      t->t->dp_fused = value != 0;
+    }
     else if (f == "keep_gradients") t->t->keep_gradients = value != 0;
     else if (f == "smooth_gradients") t->t->smooth_gradients = value != 0;
     else throw Error(B200_ERR_BAD_ARG, "unknown flag " + f);

@@ -76,5 +76,9 @@ def connect_peer_memory(trainer, dist):
     flags = [None] * world
     dist.all_gather_object(flags, ok)
     if not all(flags):
-        raise RuntimeError("peer-memory replica group: some ranks could not map their peers (set fused=False)")
+        # some rank could not map a peer (no P2P between the devices, IPC not permitted ...): every rank goes
+        # back to the NCCL all-reduce path, the replicas must not disagree about the protocol
+        if ok:
+            trainer.set_flag("dp_fused", 0)
+        return False
     return True
