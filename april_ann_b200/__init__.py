@@ -85,7 +85,8 @@ class random:  # noqa: N801  (the reference's Lua class is lower-case)
         self.h = nonnull(lib.b200h_random_new(C.c_uint32(seed)))
 
     def __del__(self):
-        if getattr(self, "h", None):
+        # (at interpreter shutdown the module globals may already be gone)
+        if getattr(self, "h", None) and lib is not None:
             lib.b200h_random_free(self.h)
             self.h = None
 
@@ -114,7 +115,8 @@ class _Component:
         self.h = nonnull(handle)
 
     def __del__(self):
-        if getattr(self, "h", None):
+        # (at interpreter shutdown the module globals may already be gone)
+        if getattr(self, "h", None) and lib is not None:
             lib.b200h_component_free(self.h)
             self.h = None
 
@@ -239,7 +241,8 @@ class supervised_trainer:  # noqa: N801
         self.is_built = False
 
     def __del__(self):
-        if getattr(self, "h", None):
+        # (at interpreter shutdown the module globals may already be gone)
+        if getattr(self, "h", None) and lib is not None:
             lib.b200h_trainer_free(self.h)
             self.h = None
 
