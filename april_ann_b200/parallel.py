@@ -22,6 +22,17 @@ def shard_rows(n, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def shard_float4(n, rank, world):
+    """Element range [lo, hi) of a tensor of n floats that `rank` owns in the peer-memory replica group:
+    the tensor is cut in float4 units, ceil(ceil(n/4) / world) per rank (csrc/dp_fused.cu, `plan`); the
+    last float4 may reach into the tensor's padding inside the arena, never past it."""
+    n4 = (n + 3) // 4
+    per = (n4 + world - 1) // world
+    lo = min(n4, rank * per)
+    hi = min(n4, lo + per)
+    return min(n, 4 * lo), min(n, 4 * hi)
+
+
 def dp_grad_scale(shared_count, global_bunch):
     """The reference's gradient smoothing with the global bunch size."""
     return 1.0 / math.sqrt(max(shared_count, 1) * global_bunch)

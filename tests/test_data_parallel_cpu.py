@@ -74,6 +74,91 @@ def _worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
+def _worker_sharded(rank, world, port, out_dir):
+    """The protocol of csrc/dp_fused.cu with gloo standing in for NVLink: every rank reduces only ITS
+    shard of every tensor (fixed rank order), applies the SGD step to that shard only (it alone keeps the
+    shard's momentum), and the updated shards are gathered into every replica."""
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group(backend="gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from april_ann_b200.parallel import shard_rows, dp_grad_scale, shard_float4
+    tr = _make_trainer()
+    x, t = _data()
+    lo, hi = shard_rows(GLOBAL_BUNCH, rank, world)
+    for _ in range(3):
+        out = tr.net.forward(x[lo:hi], True)
+        tr.net.backprop(tr.loss.gradient(out, t[lo:hi]))
+        grads, counts = {}, {}
+        tr.net.compute_gradients(grads, counts)
+        new_w = {}
+        for name in sorted(grads):
+            flat = np.ascontiguousarray(grads[name]).reshape(-1)
+            peers = [torch.empty(flat.size, dtype=torch.float32) for _ in range(world)]
+            dist.all_gather(peers, torch.from_numpy(flat.copy()))        # "peer memory": everybody's gradients
+            a, b = shard_float4(flat.size, rank, world)
+            g = np.zeros(b - a, dtype=np.float32)
+            for p in range(world):                                        # fixed rank order
+                g += peers[p].numpy()[a:b]
+            g *= np.float32(dp_grad_scale(counts.get(name, 0) or 1, GLOBAL_BUNCH))
+            # SGD on the shard only: views into the trainer's weights / momentum
+            w_sh = tr.weights[name].reshape(-1)[a:b]
+            sub_w, sub_g = {name: w_sh}, {name: g}
+            if name not in tr.optimizer.update:
+                tr.optimizer.update[name] = np.zeros_like(tr.weights[name])
+            full_u = tr.optimizer.update[name]
+            tr.optimizer.update[name] = full_u.reshape(-1)[a:b]
+            count_before = tr.optimizer.count
+            tr.optimizer.execute(sub_w, sub_g)
+            tr.optimizer.count = count_before                             # one step counter for all tensors
+            full_u.reshape(-1)[a:b] = tr.optimizer.update[name]
+            tr.optimizer.update[name] = full_u
+            new_w[name] = (a, b, w_sh.copy())
+        tr.optimizer.count += 1
+        for name in sorted(new_w):                                        # all-gather of the updated shards
+            a, b, w_sh = new_w[name]
+            spans = [None] * world
+            dist.all_gather_object(spans, (a, b, w_sh))
+            flat_w = tr.weights[name].reshape(-1)
+            for (pa, pb, pw) in spans:
+                flat_w[pa:pb] = pw
+    np.savez(os.path.join(out_dir, "shard_rank%d.npz" % rank), **tr.weights)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_shard_float4_covers_every_tensor_once():
+    from april_ann_b200.parallel import shard_float4
+    for n in (1, 3, 4, 10, 127, 128, 2048, 20480, 1605632):
+        for world in (2, 3, 4, 8):
+            spans = [shard_float4(n, r, world) for r in range(world)]
+            covered = np.zeros(n, dtype=np.int32)
+            for a, b in spans:
+                assert 0 <= a <= b <= n and (a % 4 == 0 or a == b)   # shards start on a float4 (empty ones aside)
+                covered[a:b] += 1
+            assert (covered == 1).all(), (n, world, spans)
+
+
+def test_two_rank_sharded_update_equals_single_process_step(tmp_path):
+    """reduce-scatter + SGD on the owner's shard + all-gather == all-reduce + SGD everywhere == one step on
+    the global bunch (the property the peer-memory replica group relies on)."""
+    import torch.multiprocessing as mp
+    port = _free_port()
+    mp.spawn(_worker_sharded, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    ref = _make_trainer()
+    x, t = _data()
+    for _ in range(3):
+        ref.train_step(x, t)
+    w0 = np.load(os.path.join(str(tmp_path), "shard_rank0.npz"))
+    w1 = np.load(os.path.join(str(tmp_path), "shard_rank1.npz"))
+    for name in ref.weights:
+        assert np.array_equal(w0[name], w1[name]), name
+        err = np.abs(w0[name] - ref.weights[name]).max()
+        assert err < 2e-6, (name, err)
+
+
 def test_shard_rows_partitions_every_bunch():
     from april_ann_b200.parallel import shard_rows
     for n in (1, 7, 8, 1024, 1025):
