@@ -37,7 +37,7 @@ enum {
   B200_ERR_UNSUPPORTED = 161
 };
 
-/* activation kinds (packages/ann/ann/c_src/*_actf_component.cc) */
+/* activation kinds (packages/ann/ann/c_src/<kind>_actf_component.cc) */
 enum {
   B200_ACT_NONE = 0,
   B200_ACT_LOGISTIC = 1,   /* 1/(1+e^-x);   derivative from output y(1-y), clamped */
