@@ -146,8 +146,28 @@ class _Actf:
         return ctor
 
 
-for _k in ("logistic", "tanh", "relu", "softmax", "log_softmax", "linear"):
+for _k in ("logistic", "tanh", "relu", "softmax", "log_softmax", "linear", "log_logistic", "softplus", "softsign"):
     setattr(_Actf, _k, staticmethod(_Actf._make(_k)))
+
+
+def _leaky_relu(name=None, leak=0.01, **_):
+    """ann.components.actf.leaky_relu{ leak= }  (leaky_relu_actf_component.cc)"""
+    return _Component(lib.b200h_actf_new_ex(b("leaky_relu"), b(name or ""), C.c_float(leak), C.c_float(0.0)))
+
+
+def _hardtanh(name=None, inf=-1.0, sup=1.0, **_):
+    """ann.components.actf.hardtanh{ inf=, sup= }  (hardtanh_actf_component.cc)"""
+    return _Component(lib.b200h_actf_new_ex(b("hardtanh"), b(name or ""), C.c_float(inf), C.c_float(sup)))
+
+
+def _prelu(size=0, scalar=False, name="prelu", weights=None, **_):
+    """ann.components.actf.prelu{ size=, scalar=, name=, weights= }  (prelu_actf_component.cc)"""
+    return _Component(lib.b200h_prelu_new(b(name), b(weights or name), C.c_uint(size), C.c_int(bool(scalar))))
+
+
+_Actf.leaky_relu = staticmethod(_leaky_relu)
+_Actf.hardtanh = staticmethod(_hardtanh)
+_Actf.prelu = staticmethod(_prelu)
 
 
 class components:  # noqa: N801
@@ -172,6 +192,13 @@ class components:  # noqa: N801
     @staticmethod
     def bias(size, name="b", weights=None):
         return _Component(lib.b200h_bias_new(b(name), b(weights or name), C.c_uint(size)))
+
+    @staticmethod
+    def dropout(random, prob=0.5, value=0.0, norm=True, name="dropout", size=0):
+        """ann.components.dropout{ name=, size=, prob=, value=, random=, norm= } (bind_ann_base.lua.cc:1643-1670).
+        The component continues the stream of `random` from its current state (it keeps its own copy)."""
+        return _Component(lib.b200h_dropout_new(b(name), random.h, C.c_float(prob), C.c_float(value), C.c_int(bool(norm)),
+                                                C.c_uint(size)))
 
     @staticmethod
     def rewrap(size, name="rewrap"):
@@ -208,8 +235,8 @@ class mlp:  # noqa: N801
 
 # ----------------------------------------------------------------------------- loss
 class _Loss:
-    def __init__(self, kind, size=0):
-        self.kind, self.size = kind, size
+    def __init__(self, kind, size=0, TH=0.5):
+        self.kind, self.size, self.TH = kind, size, TH
 
 
 class loss:  # noqa: N801
@@ -228,17 +255,65 @@ class loss:  # noqa: N801
         return _Loss(2, size)
 
 
+    @staticmethod
+    def zero_one(size=0, TH=0.5):
+        """ann.loss.zero_one(size, TH): 0/1 classification error, not differentiable
+        (ann/loss/c_src/zero_one_loss_function.cc:39-132)."""
+        return _Loss(3, size, TH)
+
+
+# ----------------------------------------------------------------------------- optimizers
+class _Optimizer:
+    def __init__(self, name, **options):
+        self.name, self.options = name, options
+
+
+class optimizer:  # noqa: N801
+    """ann.optimizer.*  (packages/ann/optimizer/lua_src/optimizer_{sgd,adagrad,rmsprop,adadelta}.lua)"""
+
+    @staticmethod
+    def sgd(**options):
+        return _Optimizer("sgd", **options)
+
+    @staticmethod
+    def adagrad(**options):
+        return _Optimizer("adagrad", **options)
+
+    @staticmethod
+    def rmsprop(**options):
+        return _Optimizer("rmsprop", **options)
+
+    @staticmethod
+    def adadelta(**options):
+        return _Optimizer("adadelta", **options)
+
+
 # ----------------------------------------------------------------------------- trainer
 class supervised_trainer:  # noqa: N801
     """trainable.supervised_trainer(ann_component, loss_function, bunch_size)
     -- packages/trainable/lua_src/supervised.lua:20-120."""
 
-    def __init__(self, net, loss_function, bunch_size, ctx=None):
+    def __init__(self, net, loss_function, bunch_size, optimizer=None, ctx=None):
         self.ctx = ctx or get_context()
         self.net = net
         self.bunch_size = bunch_size
+        self.loss_function = loss_function
         self.h = nonnull(lib.b200h_trainer_new(self.ctx.h, net.h, C.c_int(loss_function.kind), C.c_int(bunch_size)))
+        if loss_function.kind == 3:
+            check(lib.b200h_trainer_set_loss_threshold(self.h, C.c_float(loss_function.TH)))
         self.is_built = False
+        self.optimizer_name = "sgd"
+        if optimizer is not None:
+            self.set_optimizer(optimizer)
+
+    def set_optimizer(self, optimizer):
+        """optimizer: an ann.optimizer.* object (or its name).  Options are reset to that optimizer's
+        defaults, its state is cleared."""
+        name = optimizer if isinstance(optimizer, str) else optimizer.name
+        check(lib.b200h_trainer_set_optimizer(self.h, b(name)))
+        self.optimizer_name = name
+        for k, v in ({} if isinstance(optimizer, str) else optimizer.options).items():
+            self.set_option(k, v)
 
     def __del__(self):
         # (at interpreter shutdown the module globals may already be gone)
@@ -332,12 +407,16 @@ class supervised_trainer:  # noqa: N801
                 x.shape[1], self.get_input_size(), t.shape[1], self.get_output_size()))
         return x, t
 
-    def train_step(self, input, target):  # noqa: A002
-        """-> (bunch mean loss, per-pattern loss vector)  supervised.lua:725-821"""
+    def train_step(self, input, target, bunch_size=None, max_gradients_norm=None):  # noqa: A002
+        """-> (bunch mean loss, per-pattern loss vector)  supervised.lua:725-821.
+        bunch_size: the value of the gradient smoothing 1/sqrt(shared_count * bunch_size); as in the
+        reference it defaults to the TRAINER's bunch_size, not to the row count of `input`
+        (supervised.lua:757).  max_gradients_norm: global gradient-norm clip (supervised.lua:805-811)."""
         x, t = self._bunch(input, target)
         rows = np.empty(x.shape[0], dtype=_f32)
         l = C.c_float()
-        check(lib.b200h_trainer_train_step(self.h, fptr(x), fptr(t), C.c_int(x.shape[0]), C.byref(l), fptr(rows)))
+        check(lib.b200h_trainer_train_step_ex(self.h, fptr(x), fptr(t), C.c_int(x.shape[0]), C.c_int(int(bunch_size or 0)),
+                                              C.c_double(float(max_gradients_norm or 0.0)), C.byref(l), fptr(rows)))
         return l.value, rows
 
     def validate_step(self, input, target):  # noqa: A002
@@ -372,6 +451,47 @@ class supervised_trainer:  # noqa: N801
         y = np.empty((x.shape[0], self.get_output_size()), dtype=_f32)
         check(lib.b200h_trainer_calculate(self.h, fptr(x), C.c_int(x.shape[0]), fptr(y)))
         return y
+
+    def use_dataset(self, input_dataset):
+        """forward only over a dataset, bunch by bunch -> [n, output_size]  (supervised.lua:1291-1430)"""
+        x = _as_f32(input_dataset)
+        x = x.reshape(x.shape[0], -1)
+        if x.shape[1] != self.get_input_size():
+            raise B200Error(128, "Incorrect patternSize: input %d (expected %d)" % (x.shape[1], self.get_input_size()))
+        y = np.empty((x.shape[0], self.get_output_size()), dtype=_f32)
+        check(lib.b200h_trainer_use_dataset(self.h, fptr(x), C.c_int(x.shape[0]), fptr(y)))
+        return y
+
+    # -- checkpoint / resume (optimizer_sgd.lua:102-119: options + count + update; supervised.lua:349-395) ------
+    def get_count(self):
+        c = C.c_int64()
+        check(lib.b200h_trainer_get_count(self.h, C.byref(c)))
+        return c.value
+
+    def set_count(self, count):
+        check(lib.b200h_trainer_set_count(self.h, C.c_int64(int(count))))
+
+    def optimizer_state(self, name, which):
+        """which: 2 = update (sgd momentum buffer / rmsprop Eupdates / adadelta update), 3 = Egradients / Erms,
+        4 = adadelta Eupdates"""
+        return self._get(name, which)
+
+    def state_dict(self):
+        """Everything a resumed run needs, as host arrays: weights, optimizer state tensors, count, options."""
+        kinds = {"sgd": (2,), "adagrad": (3,), "rmsprop": (2, 3), "adadelta": (2, 3, 4)}[self.optimizer_name]
+        return {"optimizer": self.optimizer_name, "count": self.get_count(),
+                "weights": {n: self.weights(n) for n in self.weight_names()},
+                "state": {k: {n: self._get(n, k) for n in self.weight_names()} for k in kinds}}
+
+    def load_state_dict(self, sd):
+        if sd["optimizer"] != self.optimizer_name:
+            raise B200Error(128, "checkpoint of optimizer %s loaded into %s" % (sd["optimizer"], self.optimizer_name))
+        for n, w in sd["weights"].items():
+            self.set_weights(n, w)
+        for k, d in sd["state"].items():
+            for n, v in d.items():
+                self.set_weights(n, v, which=int(k))
+        self.set_count(sd["count"])
 
     def component_token(self, component, which="output"):
         """get_input/get_output/get_error_input/get_error_output of a named component after

@@ -43,7 +43,7 @@ lib.b200_last_error_string.restype = C.c_char_p
 lib.b200_stream.restype = C.c_void_p
 lib.b200_stream.argtypes = [C.c_void_p]
 for _n in ("b200h_random_new", "b200h_stack_new", "b200h_hyperplane_new", "b200h_dot_product_new",
-           "b200h_bias_new", "b200h_actf_new", "b200h_rewrap_new", "b200h_flatten_new",
+           "b200h_bias_new", "b200h_actf_new", "b200h_actf_new_ex", "b200h_prelu_new", "b200h_dropout_new", "b200h_rewrap_new", "b200h_flatten_new",
            "b200h_convolution_new", "b200h_convolution_bias_new", "b200h_max_pooling_new",
            "b200h_mlp_generate", "b200h_trainer_new"):
     getattr(lib, _n).restype = C.c_void_p

@@ -17,6 +17,7 @@ int gemm_dispatch(b200_ctx *ctx, int transA, int transB, int M, int N, int K, co
 extern "C" int b200_sgemm(b200_ctx *ctx, int transA, int transB, int M, int N, int K, float alpha,
                           const float *A, int lda, const float *B, int ldb, float beta, float *C,
                           int ldc) {
+  B200_ENTER(ctx);
   ARG_CHECK(ctx && A && B && C, "NULL pointer");
   ARG_CHECK(M >= 0 && N >= 0 && K >= 0, "negative dimension");
   ARG_CHECK(lda >= (transA ? M : K) && ldb >= (transB ? K : N) && ldc >= N, "leading dimension too small");
@@ -29,6 +30,7 @@ extern "C" int b200_sgemm(b200_ctx *ctx, int transA, int transB, int M, int N, i
 // y[M or N] = alpha * op(A) x + beta*y, A is MxN row-major (gemv.cu:44)
 extern "C" int b200_sgemv(b200_ctx *ctx, int transA, int M, int N, float alpha, const float *A,
                           int lda, const float *x, int incx, float beta, float *y, int incy) {
+  B200_ENTER(ctx);
   ARG_CHECK(ctx && A && x && y, "NULL pointer");
   ARG_CHECK(incx >= 1 && incy >= 1 && lda >= N, "bad stride");
   GemmEpilogue ep;
@@ -42,6 +44,7 @@ extern "C" int b200_sgemv(b200_ctx *ctx, int transA, int M, int N, float alpha, 
 // A[M,N] += alpha * x y^T (ger.cu:42)
 extern "C" int b200_sger(b200_ctx *ctx, int M, int N, float alpha, const float *x, int incx,
                          const float *y, int incy, float *A, int lda) {
+  B200_ENTER(ctx);
   ARG_CHECK(ctx && A && x && y, "NULL pointer");
   ARG_CHECK(incx >= 1 && incy >= 1 && lda >= N, "bad stride");
   GemmEpilogue ep;
@@ -54,6 +57,7 @@ extern "C" int b200_sger(b200_ctx *ctx, int M, int N, float alpha, const float *
 extern "C" int b200_linear_fwd(b200_ctx *ctx, int M, int N, int K, const float *X, int ldx,
                                const float *W, int ldw, const float *bias, int act, float *Y,
                                int ldy) {
+  B200_ENTER(ctx);
   ARG_CHECK(ctx && X && W && Y, "NULL pointer");
   ARG_CHECK(act == B200_ACT_NONE || act == B200_ACT_LOGISTIC || act == B200_ACT_TANH ||
                 act == B200_ACT_RELU || act == B200_ACT_LINEAR,
@@ -70,6 +74,7 @@ extern "C" int b200_linear_fwd(b200_ctx *ctx, int M, int N, int K, const float *
 extern "C" int b200_linear_bwd_data(b200_ctx *ctx, int M, int N, int K, const float *dY, int lddy,
                                     const float *W, int ldw, int act_prev, const float *Yprev,
                                     int ldyp, float *dX, int lddx) {
+  B200_ENTER(ctx);
   ARG_CHECK(ctx && dY && W && dX, "NULL pointer");
   const bool has_prev = (act_prev == B200_ACT_LOGISTIC || act_prev == B200_ACT_TANH || act_prev == B200_ACT_RELU);
   if (has_prev) ARG_CHECK(Yprev, "Yprev is required when act_prev is set");
@@ -88,6 +93,7 @@ extern "C" int b200_linear_bwd_data(b200_ctx *ctx, int M, int N, int K, const fl
 extern "C" int b200_linear_bwd_weight(b200_ctx *ctx, int M, int N, int K, const float *dY, int lddy,
                                       const float *X, int ldx, float scale, float beta, float *dW,
                                       int lddw, float *db) {
+  B200_ENTER(ctx);
   ARG_CHECK(ctx && dY && X && dW, "NULL pointer");
   if (skinny_applicable(M, N, K)) return skinny_bwd_weight(ctx, M, N, K, dY, lddy, X, ldx, scale, beta, dW, lddw, db);
   GemmEpilogue ep;

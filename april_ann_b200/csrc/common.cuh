@@ -40,6 +40,7 @@ struct b200_ctx {
   // scratch for reductions / split-K etc.
   void *scratch[kBranches + 1] = {};      // one per branch (+ main): concurrent branches must not share it
   size_t scratch_bytes[kBranches + 1] = {};
+  std::vector<void *> retired_scratch;    // outgrown scratch blocks that captured graphs may still reference
   // NCCL (dlopen'ed lazily)
   void *nccl_comm = nullptr;
   int nranks = 1, rank = 0;
@@ -68,13 +69,30 @@ void *b200_scratch(b200_ctx *ctx, size_t bytes);
 // carve-out as the contraction (maximum shared memory): CTAs of kernels with different carve-outs are not
 // co-scheduled on one SM, and with the default preference these kernels only got the SMs a contraction
 // left idle.  Call once per kernel, before its launch.
+// (function attributes belong to the device's context: the "already done" flags are kept per device, so
+// that one process may drive several devices -- one host thread over N contexts, or a thread per device)
+#define B200_MAX_DEVICES 64
+#define ONCE_PER_DEVICE(ctx)                                          \
+  ([&]() -> bool {                                                    \
+    static bool _done[B200_MAX_DEVICES];                              \
+    const int _d = (ctx)->device & (B200_MAX_DEVICES - 1);            \
+    const bool _first = !_done[_d];                                   \
+    _done[_d] = true;                                                 \
+    return _first;                                                    \
+  }())
 #define PREFER_MAX_SMEM_ONCE(kernel)                                                                          \
   do {                                                                                                        \
-    static bool _done = false;                                                                                \
-    if (!_done) {                                                                                             \
+    if (ONCE_PER_DEVICE(ctx))                                                                                 \
       cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); \
-      _done = true;                                                                                           \
-    }                                                                                                         \
+  } while (0)
+// every C-ABI entry point that launches or allocates makes the context's device current first
+int b200_make_current(b200_ctx *ctx);
+#define B200_ENTER(ctx)                                \
+  do {                                                 \
+    if (ctx) {                                         \
+      int _st = b200_make_current(ctx);                \
+      if (_st) return _st;                             \
+    }                                                  \
   } while (0)
 
 #define ARG_CHECK(cond, msg)                                                  \

@@ -260,6 +260,7 @@ int set_smem(K kernel, size_t bytes) {
 
 extern "C" int b200_conv2d_fwd(b200_ctx *ctx, int B, int C, int H, int W, int n, int kh, int kw, int sh, int sw,
                                const float *x, const float *w, const float *bias, int act, float *y) {
+  B200_ENTER(ctx);
   ARG_CHECK(ctx && x && w && y, "NULL pointer");
   ARG_CHECK(B > 0 && C > 0 && n > 0 && kh > 0 && kw > 0 && sh > 0 && sw > 0 && H >= kh && W >= kw, "bad geometry");
   const int oH = (H - kh) / sh + 1, oW = (W - kw) / sw + 1;
@@ -275,6 +276,7 @@ extern "C" int b200_conv2d_fwd(b200_ctx *ctx, int B, int C, int H, int W, int n,
 
 extern "C" int b200_conv2d_bwd_data(b200_ctx *ctx, int B, int C, int H, int W, int n, int kh, int kw, int sh, int sw,
                                     const float *dy, const float *w, float *dx) {
+  B200_ENTER(ctx);
   ARG_CHECK(ctx && dy && w && dx, "NULL pointer");
   ARG_CHECK(B > 0 && C > 0 && n > 0 && kh > 0 && kw > 0 && sh > 0 && sw > 0 && H >= kh && W >= kw, "bad geometry");
   const int oH = (H - kh) / sh + 1, oW = (W - kw) / sw + 1;
@@ -290,6 +292,7 @@ extern "C" int b200_conv2d_bwd_data(b200_ctx *ctx, int B, int C, int H, int W, i
 extern "C" int b200_conv2d_bwd_weight(b200_ctx *ctx, int B, int C, int H, int W, int n, int kh, int kw, int sh,
                                       int sw, const float *dy, const float *x, float scale, float beta, float *dw,
                                       float *db) {
+  B200_ENTER(ctx);
   ARG_CHECK(ctx && dy && x && dw, "NULL pointer");
   ARG_CHECK(B > 0 && C > 0 && n > 0 && kh > 0 && kw > 0 && sh > 0 && sw > 0 && H >= kh && W >= kw, "bad geometry");
   const int oH = (H - kh) / sh + 1, oW = (W - kw) / sw + 1;
@@ -318,6 +321,7 @@ extern "C" int b200_conv2d_bwd_weight(b200_ctx *ctx, int B, int C, int H, int W,
 }
 
 extern "C" int b200_conv_bias_fwd(b200_ctx *ctx, int B, int n, int HW, const float *x, const float *bias, float *y) {
+  B200_ENTER(ctx);
   ARG_CHECK(ctx && x && bias && y, "NULL pointer");
   const size_t total = (size_t)B * n * HW;
   if (!total) return B200_OK;
@@ -327,6 +331,7 @@ extern "C" int b200_conv_bias_fwd(b200_ctx *ctx, int B, int n, int HW, const flo
 }
 extern "C" int b200_conv_bias_grad(b200_ctx *ctx, int B, int n, int HW, const float *dy, float scale, float beta,
                                    float *db) {
+  B200_ENTER(ctx);
   ARG_CHECK(ctx && dy && db, "NULL pointer");
   if (n <= 0) return B200_OK;
   int chunks = (2 * ctx->sm_count + n - 1) / n;   // ~2 CTAs per SM in all
@@ -345,6 +350,7 @@ extern "C" int b200_conv_bias_grad(b200_ctx *ctx, int B, int n, int HW, const fl
 
 extern "C" int b200_maxpool_fwd(b200_ctx *ctx, int B, int C, int H, int W, int kh, int kw, int sh, int sw,
                                 const float *x, float *y, int32_t *argmax) {
+  B200_ENTER(ctx);
   ARG_CHECK(ctx && x && y, "NULL pointer");
   ARG_CHECK(kh > 0 && kw > 0 && sh > 0 && sw > 0 && H >= kh && W >= kw, "bad geometry");
   ARG_CHECK((size_t)B * C * H * W < (size_t)INT32_MAX, "tensor too large for int32 positions");
@@ -357,6 +363,7 @@ extern "C" int b200_maxpool_fwd(b200_ctx *ctx, int B, int C, int H, int W, int k
 }
 extern "C" int b200_maxpool_bwd(b200_ctx *ctx, int B, int C, int H, int W, int kh, int kw, int sh, int sw,
                                 const float *dy, const int32_t *argmax, float *dx) {
+  B200_ENTER(ctx);
   ARG_CHECK(ctx && dy && argmax && dx, "NULL pointer");
   const int oH = (H - kh) / sh + 1, oW = (W - kw) / sw + 1;
   const size_t total = (size_t)B * C * H * W;

@@ -318,6 +318,7 @@ __global__ void dp_wait_kernel(const b200_dp_group grp, int nbuckets, const int6
 }  // namespace
 
 extern "C" int b200_ipc_export(b200_ctx *ctx, void *dptr, void *handle64) {
+  B200_ENTER(ctx);
   ARG_CHECK(ctx && dptr && handle64, "NULL pointer");
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
   cudaIpcMemHandle_t h;
@@ -326,6 +327,7 @@ extern "C" int b200_ipc_export(b200_ctx *ctx, void *dptr, void *handle64) {
   return B200_OK;
 }
 extern "C" int b200_ipc_import(b200_ctx *ctx, const void *handle64, void **dptr) {
+  B200_ENTER(ctx);
   ARG_CHECK(ctx && handle64 && dptr, "NULL pointer");
   cudaIpcMemHandle_t h;
   memcpy(&h, handle64, 64);
@@ -334,6 +336,7 @@ extern "C" int b200_ipc_import(b200_ctx *ctx, const void *handle64, void **dptr)
   return B200_OK;
 }
 extern "C" int b200_ipc_close(b200_ctx *ctx, void *dptr) {
+  B200_ENTER(ctx);
   ARG_CHECK(ctx, "NULL pointer");
   if (dptr) CUDA_TRY(cudaIpcCloseMemHandle(dptr));
   return B200_OK;
@@ -343,6 +346,7 @@ extern "C" size_t b200_dp_debug_offset(void) { return sizeof(long long) * 2 * DP
 
 extern "C" int b200_dp_fused_update(b200_ctx *ctx, const b200_dp_group *grp, int ntensors, const b200_sgd_tensor *tensors_dev,
                                     const b200_sgd_tensor *tensors_host, double decay, int64_t *count_dev, int bucket) {
+  B200_ENTER(ctx);
   ARG_CHECK(ctx && grp && tensors_dev && tensors_host && count_dev, "NULL pointer");
   ARG_CHECK(grp->nranks >= 2 && grp->nranks <= B200_DP_MAX_RANKS && grp->rank >= 0 && grp->rank < grp->nranks, "bad replica group");
   ARG_CHECK(bucket >= 0 && bucket < DP_MAX_BUCKETS, "bucket out of range");
@@ -390,8 +394,7 @@ extern "C" int b200_dp_fused_update(b200_ctx *ctx, const b200_dp_group *grp, int
 #define DP_LAUNCH_SHARD(NR, UN)                                                                                   \
   do {                                                                                                            \
     auto kern = dp_shard_update_kernel<NR, UN>;                                                                   \
-    static bool attr = false;                                                                                     \
-    if (!attr) { CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DP_SMEM)); attr = true; } \
+    if (ONCE_PER_DEVICE(ctx)) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DP_SMEM)); \
     size_t blocks = (n4 + (size_t)DP_THREADS * UN - 1) / ((size_t)DP_THREADS * UN);                              \
     if (blocks > (size_t)sms) blocks = (size_t)sms;                                                               \
     if (blocks < 1) blocks = 1;                                                                                   \
@@ -417,8 +420,7 @@ extern "C" int b200_dp_fused_update(b200_ctx *ctx, const b200_dp_group *grp, int
 #define DP_LAUNCH(NR, UN)                                                                                         \
   do {                                                                                                            \
     auto kern = dp_fused_update_kernel<NR, UN>;                                                                   \
-    static bool attr = false;                                                                                     \
-    if (!attr) { CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DP_SMEM)); attr = true; } \
+    if (ONCE_PER_DEVICE(ctx)) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DP_SMEM)); \
     size_t blocks = (shard4 + (size_t)DP_THREADS * UN - 1) / ((size_t)DP_THREADS * UN);                          \
     if (blocks > (size_t)sms) blocks = (size_t)sms;                                                               \
     if (blocks < 1) blocks = 1;                                                                                   \
@@ -433,6 +435,7 @@ extern "C" int b200_dp_fused_update(b200_ctx *ctx, const b200_dp_group *grp, int
 }
 
 extern "C" int b200_dp_wait(b200_ctx *ctx, const b200_dp_group *grp, int nbuckets, const int64_t *count_dev) {
+  B200_ENTER(ctx);
   ARG_CHECK(ctx && grp && count_dev, "NULL pointer");
   ARG_CHECK(nbuckets >= 0 && nbuckets <= DP_MAX_BUCKETS, "bucket count out of range");
   if (nbuckets == 0) return B200_OK;

@@ -180,6 +180,7 @@ __global__ void __launch_bounds__(TPB) gather_rows_kernel(int nrows, int cols, c
 }  // namespace
 
 extern "C" int b200_actf_fwd(b200_ctx *ctx, int act, size_t n, const float *x, float *y) {
+  B200_ENTER(ctx);
   ARG_CHECK(ctx && x && y, "NULL pointer");
   ARG_CHECK(act == B200_ACT_LOGISTIC || act == B200_ACT_TANH || act == B200_ACT_RELU ||
                 act == B200_ACT_LINEAR || act == B200_ACT_NONE,
@@ -187,34 +188,42 @@ extern "C" int b200_actf_fwd(b200_ctx *ctx, int act, size_t n, const float *x, f
   return launch_map1(ctx, n, x, y, ActFwd{act == B200_ACT_LINEAR ? B200_ACT_NONE : act});
 }
 extern "C" int b200_actf_bwd(b200_ctx *ctx, int act, size_t n, const float *y, const float *dy, float *dx) {
+  B200_ENTER(ctx);
   ARG_CHECK(ctx && y && dy && dx, "NULL pointer");
   return launch_map2(ctx, n, y, dy, dx, ActBwd{act == B200_ACT_LINEAR ? B200_ACT_NONE : act});
 }
 extern "C" int b200_saxpy(b200_ctx *ctx, size_t n, float alpha, const float *x, float *y) {
+  B200_ENTER(ctx);
   ARG_CHECK(ctx && x && y, "NULL pointer");
   return launch_map2(ctx, n, x, y, y, Axpy{alpha});
 }
 extern "C" int b200_sscal(b200_ctx *ctx, size_t n, float alpha, float *x) {
+  B200_ENTER(ctx);
   ARG_CHECK(ctx && x, "NULL pointer");
   return launch_map1(ctx, n, x, x, Scal{alpha});
 }
 extern "C" int b200_scopy(b200_ctx *ctx, size_t n, const float *x, float *y) {
+  B200_ENTER(ctx);
   ARG_CHECK(ctx && x && y, "NULL pointer");
   return launch_map1(ctx, n, x, y, Ident{});
 }
 extern "C" int b200_cmul(b200_ctx *ctx, size_t n, const float *x, float *y) {
+  B200_ENTER(ctx);
   ARG_CHECK(ctx && x && y, "NULL pointer");
   return launch_map2(ctx, n, x, y, y, Mul{});
 }
 extern "C" int b200_sum(b200_ctx *ctx, size_t n, const float *x, float *out) {
+  B200_ENTER(ctx);
   ARG_CHECK(ctx && x && out, "NULL pointer");
   return reduce_impl<false, false>(ctx, n, x, out);
 }
 extern "C" int b200_nrm2sq(b200_ctx *ctx, size_t n, const float *x, float *out) {
+  B200_ENTER(ctx);
   ARG_CHECK(ctx && x && out, "NULL pointer");
   return reduce_impl<true, true>(ctx, n, x, out);
 }
 extern "C" int b200_bias_fwd(b200_ctx *ctx, int M, int N, const float *x, const float *b, float *y) {
+  B200_ENTER(ctx);
   ARG_CHECK(ctx && x && b && y, "NULL pointer");
   if (M <= 0 || N <= 0) return B200_OK;
   bias_fwd_kernel<<<grid_for((size_t)M * N, ctx->sm_count), TPB, 0, ctx->stream>>>(M, N, x, b, y);
@@ -223,12 +232,14 @@ extern "C" int b200_bias_fwd(b200_ctx *ctx, int M, int N, const float *x, const 
 }
 extern "C" int b200_bias_grad(b200_ctx *ctx, int M, int N, const float *dy, int lddy, float scale,
                               float beta, float *db) {
+  B200_ENTER(ctx);
   ARG_CHECK(ctx && dy && db, "NULL pointer");
   if (N <= 0) return B200_OK;
   // db[n] = beta*db[n] + scale * sum_m dy[m,n]  (bias_component.cc:87-122): two-stage column sum, skinny.cu
   return colsum_scaled(ctx, M, N, dy, lddy, scale, beta, db);
 }
 extern "C" int b200_loss_accumulate(b200_ctx *ctx, int M, const float *loss_rows, double *stats) {
+  B200_ENTER(ctx);
   ARG_CHECK(ctx && loss_rows && stats, "NULL pointer");
   PREFER_MAX_SMEM_ONCE(loss_accumulate_kernel);
   loss_accumulate_kernel<<<1, 256, 0, ctx->stream>>>(M, loss_rows, stats);
@@ -236,6 +247,7 @@ extern "C" int b200_loss_accumulate(b200_ctx *ctx, int M, const float *loss_rows
   return B200_OK;
 }
 extern "C" int b200_counter_increment(b200_ctx *ctx, int64_t *count_dev) {
+  B200_ENTER(ctx);
   ARG_CHECK(ctx && count_dev, "NULL pointer");
   counter_increment_kernel<<<1, 1, 0, ctx->stream>>>(count_dev);
   LAUNCH_CHECK(ctx);
@@ -243,6 +255,7 @@ extern "C" int b200_counter_increment(b200_ctx *ctx, int64_t *count_dev) {
 }
 extern "C" int b200_gather_rows(b200_ctx *ctx, int nrows, int cols, const float *data, const int32_t *idx,
                                 float *out) {
+  B200_ENTER(ctx);
   ARG_CHECK(ctx && data && idx && out, "NULL pointer");
   if (nrows <= 0 || cols <= 0) return B200_OK;
   const bool vec = (cols % 4 == 0) && aligned16(data) && aligned16(out);

@@ -921,10 +921,12 @@ void gemm_tc_destroy(b200_ctx *ctx) {
 
 // debug hook: per-CTA clock64 stamps (device buffer of 8*grid int64, or NULL to switch off)
 extern "C" int b200_debug_tc_stamps(b200_ctx *ctx, long long *stamps_dev) {
+  B200_ENTER(ctx);
   state(ctx)->stamps = stamps_dev;
   return B200_OK;
 }
 extern "C" int b200_debug_tc_stages(b200_ctx *ctx, int stages) {
+  B200_ENTER(ctx);
   state(ctx)->force_stages = stages & 0xff;
   state(ctx)->dbg_flags = (uint32_t)stages >> 8;
   return B200_OK;
@@ -932,6 +934,7 @@ extern "C" int b200_debug_tc_stages(b200_ctx *ctx, int stages) {
 
 // debug hook: override descriptor fields {a_lbo,a_sbo,a_layout,a_kstep,b_lbo,b_sbo,b_layout,b_kstep}
 extern "C" int b200_debug_tc_override(b200_ctx *ctx, int enable, const uint32_t *vals8, int force_bn) {
+  B200_ENTER(ctx);
   TcState *s = state(ctx);
   s->dbg_on = enable != 0;
   if (vals8) memcpy(s->dbg, vals8, sizeof(s->dbg));

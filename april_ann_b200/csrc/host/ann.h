@@ -36,6 +36,12 @@ class MTRand {
   uint32_t randInt(uint32_t n);          // [0, n]
   double rand(double n = 1.0);           // [0, n]
   void shuffle(int size, int *out);      // 0-based permutation
+  // 624 state words (after the last reload) + index of the next unread word: what the device-side
+  // generator of the dropout mask continues from
+  void exportState(uint32_t *words624, int32_t *next) const {
+    for (int i = 0; i < 624; ++i) words624[i] = state[i];
+    *next = left == 0 ? 624 : pos;
+  }
  private:
   void reload();
   uint32_t state[624];
@@ -146,15 +152,50 @@ class BiasANNComponent : public ANNComponent {
 
 class ActivationFunctionANNComponent : public ANNComponent {
  public:
-  ActivationFunctionANNComponent(const std::string &name, int act);
+  ActivationFunctionANNComponent(const std::string &name, int act, float p0 = 0.0f, float p1 = 0.0f);
   MatrixPtr doForward(const MatrixPtr &input, bool during_training) override;
   MatrixPtr doBackprop(const MatrixPtr &error_input) override;
   const char *kind() const override { return "actf"; }
   void build(unsigned in, unsigned out, MatrixDict &weights, ComponentDict &components) override;
+  // fusable into the epilogue of the contraction that feeds it
   bool elementwise() const {
     return act == B200_ACT_LOGISTIC || act == B200_ACT_TANH || act == B200_ACT_RELU || act == B200_ACT_LINEAR;
   }
+  bool rowwise() const { return act == B200_ACT_SOFTMAX || act == B200_ACT_LOG_SOFTMAX; }
   int act;
+  float p0, p1;   // leaky_relu: leak ; hardtanh: inf, sup
+};
+
+// prelu_actf_component.cc: y = x>0 ? x : a*x with a learnable a[size,1] (scalar: [1,1])
+class PReLUActfANNComponent : public ANNComponent {
+ public:
+  PReLUActfANNComponent(const std::string &name, const std::string &wname, unsigned size, bool scalar);
+  MatrixPtr doForward(const MatrixPtr &input, bool during_training) override;
+  MatrixPtr doBackprop(const MatrixPtr &error_input) override;
+  void computeAllGradients(MatrixDict &grads) override;
+  void reset(unsigned it = 0) override;
+  void build(unsigned in, unsigned out, MatrixDict &weights, ComponentDict &components) override;
+  const char *kind() const override { return "prelu"; }
+  int sharedCountContribution() const override { return 1; }
+  bool scalar;
+  MatrixPtr weights_matrix;
+};
+
+// dropout_component.cc:67-134.  The mask is drawn on the device from the component's own MT19937 stream
+// (the state of the `random` object given at construction is copied at the first training forward).
+class DropoutANNComponent : public ANNComponent {
+ public:
+  DropoutANNComponent(const std::string &name, const MTRand &random, float prob, float value, bool norm, unsigned size);
+  ~DropoutANNComponent();
+  MatrixPtr doForward(const MatrixPtr &input, bool during_training) override;
+  MatrixPtr doBackprop(const MatrixPtr &error_input) override;
+  void build(unsigned in, unsigned out, MatrixDict &weights, ComponentDict &components) override;
+  const char *kind() const override { return "dropout"; }
+  MTRand random;
+  float prob, value;
+  bool normalize_after_training;
+  void *mt_dev = nullptr;
+  MatrixPtr mask;
 };
 
 class RewrapANNComponent : public ANNComponent {
@@ -210,14 +251,14 @@ class ConvolutionBiasANNComponent : public ANNComponent {
 class MaxPoolingANNComponent : public ANNComponent {
  public:
   MaxPoolingANNComponent(const std::string &name, const std::vector<int> &kernel, const std::vector<int> &step);
-  ~MaxPoolingANNComponent();
   MatrixPtr doForward(const MatrixPtr &input, bool during_training) override;
   MatrixPtr doBackprop(const MatrixPtr &error_input) override;
   void reset(unsigned it = 0) override;
   const char *kind() const override { return "max_pooling"; }
   std::vector<int> kernel, step;
-  int32_t *argmax = nullptr;
-  size_t argmax_n = 0;
+  // int32 positions of the selected inputs (maxpooling_component.cc:166-189), one block per forward pass,
+  // allocated like an activation: a captured step graph keeps its own block alive (Graph::keep)
+  MatrixPtr argmax;
 };
 
 // stack_component.cc:81-104, with hyperplane_component.cc:77-97 flattened into it.
@@ -282,7 +323,7 @@ std::shared_ptr<StackANNComponent> mlpAllAllGenerate(const std::string &topology
 int actfFromName(const std::string &kind);   // throws on unknown names
 
 // ---------------------------------------------------------------- loss
-enum LossKind { LOSS_MSE = 0, LOSS_CROSS_ENTROPY = 1, LOSS_MULTI_CLASS_CROSS_ENTROPY = 2 };
+enum LossKind { LOSS_MSE = 0, LOSS_CROSS_ENTROPY = 1, LOSS_MULTI_CLASS_CROSS_ENTROPY = 2, LOSS_ZERO_ONE = 3 };
 
 class LossFunction {
  public:
@@ -299,14 +340,20 @@ class LossFunction {
   void reset();
   int kind;
   unsigned size;
+  float TH = 0.5f;               // zero_one: decision threshold of the two-class case
   b200_ctx *ctx;
   double *stats_dev = nullptr;   // sum, sum of squares, count
 };
 
 // ---------------------------------------------------------------- optimizer
+// ann.optimizer.{sgd,adagrad,rmsprop,adadelta}: option tables with the reference's defaults
+// (optimizer_sgd.lua:39-47, optimizer_adagrad.lua:20-40, optimizer_rmsprop.lua:20-42, optimizer_adadelta.lua:20-44)
 class SGDOptimizer {
  public:
   SGDOptimizer();
+  int kind = B200_OPT_SGD;
+  void setKind(int kind);               // resets the options to that optimizer's defaults
+  bool validOption(const std::string &name) const;
   void setOption(const std::string &name, double v);
   double getOption(const std::string &name) const;
   void setLayerwiseOption(const std::string &layer, const std::string &name, double v);
@@ -329,10 +376,24 @@ class SupervisedTrainer {
                         const std::string &name_match);
   // one training step on a device-resident bunch; returns nothing on the host (the per-row
   // losses stay on the device in last_loss_rows).  supervised.lua:725-821
-  void trainStepDevice(const MatrixPtr &x, const MatrixPtr &t);
+  // smoothing_bunch: the bunch_size of supervised.lua:757,800 (0 = the trainer's bunch_size);
+  // max_gradients_norm: the global-norm clip of supervised.lua:805-811 (0 = off)
+  void trainStepDevice(const MatrixPtr &x, const MatrixPtr &t, int smoothing_bunch = 0, double max_gradients_norm = 0.0);
   void validateStepDevice(const MatrixPtr &x, const MatrixPtr &t);
   // host-pointer API: H2D of the bunch, step, D2H of the bunch-mean loss
-  float trainStep(const float *x, const float *t, int bunch, float *loss_rows_out);
+  float trainStep(const float *x, const float *t, int bunch, float *loss_rows_out, int smoothing_bunch = 0,
+                  double max_gradients_norm = 0.0);
+  // use_dataset (supervised.lua:1291-1430): forward only, bunch by bunch, outputs to the host
+  void useDataset(const float *x, int n, float *y);
+  // checkpoint / resume of the optimizer state (optimizer_sgd.lua:102-119 exports options + count + update)
+  int64_t getCount();
+  void setCount(int64_t c);
+  void setOptimizer(int kind);
+  void invalidateGraphs();
+  void sgd_dirty_public() { sgd_dirty = true; }
+  void ensureOptimizerState() { if (sgd_dirty || (optimizer.kind != B200_OPT_SGD && !state1_arena)) uploadSgdTable(); }
+  MatrixDict state1, state2;            // adagrad Egradients / rmsprop Erms / adadelta Egradients ; adadelta Eupdates
+  MatrixPtr state1_arena, state2_arena;
   float validateStep(const float *x, const float *t, int bunch, float *loss_rows_out);
   // dataset loops (supervised.lua:1149-1226, trainable.lua:95-330): the dataset is uploaded
   // once, bunches are gathered on the device, the epoch mean is read back once.
@@ -382,7 +443,12 @@ class SupervisedTrainer {
   size_t numParameters() const { return total_params; }
 
  private:
-  void runStep(const MatrixPtr &x, const MatrixPtr &t, int global_bunch);
+  void runStep(const MatrixPtr &x, const MatrixPtr &t, int global_bunch, double max_gradients_norm);
+  void runUpdateSimple(double max_gradients_norm);
+  bool dpBucketPlan(std::vector<std::pair<int, int>> *out);
+  b200_opt_tensor *opt_dev = nullptr;
+  std::vector<b200_opt_tensor> opt_host;
+  float *norm_dev = nullptr;
   MatrixPtr outputLayerFused(const MatrixPtr &h, const MatrixPtr &t, bool training, MatrixPtr &logp, MatrixPtr &rows,
                              MatrixPtr &grad);
   void uploadSgdTable();
@@ -405,7 +471,9 @@ class SupervisedTrainer {
   bool slot_trained[2] = {false, false};
   int next_slot = 0, staged_slot = -1;
   struct Graph;
-  std::map<std::pair<int, const float *>, Graph *> graphs;   // (bunch size, input buffer) -> captured step
+  // (bunch rows, smoothing bunch, input buffer) -> captured step
+  std::map<std::pair<std::pair<int, int>, const float *>, Graph *> graphs;
+  double graph_max_norm = 0.0;          // the clip threshold baked into the captured graphs
 };
 
 bool luaPatternMatch(const std::string &pattern, const std::string &s);

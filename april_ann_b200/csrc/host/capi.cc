@@ -43,6 +43,11 @@ b200_random *b200h_random_new(uint32_t seed) { return new b200_random(seed); }
 void b200h_random_free(b200_random *r) { delete r; }
 double b200h_random_rand(b200_random *r, double n) { return r->r.rand(n); }
 uint32_t b200h_random_randint(b200_random *r, uint32_t n) { return r->r.randInt(n); }
+int b200h_random_export_state(b200_random *r, uint32_t *words624, int32_t *next) {
+  if (!r || !words624 || !next) { b200_set_error("random export_state: NULL"); return B200_ERR_BAD_ARG; }
+  r->r.exportState(words624, next);
+  return B200_OK;
+}
 int b200h_random_shuffle(b200_random *r, int size, int *out) {
   if (!r || !out || size <= 0) { b200_set_error("random shuffle: size must be >= 0"); return B200_ERR_BAD_ARG; }
   r->r.shuffle(size, out);
@@ -70,7 +75,25 @@ b200_component *b200h_bias_new(const char *name, const char *weights, unsigned s
   return make([&] { return std::make_shared<BiasANNComponent>(str(name), str(weights), size); });
 }
 b200_component *b200h_actf_new(const char *kind, const char *name) {
-  return make([&] { return std::make_shared<ActivationFunctionANNComponent>(str(name), actfFromName(str(kind))); });
+  return make([&] {
+    const int act = actfFromName(str(kind));
+    // defaults of the bindings: leaky_relu leak 0.01, hardtanh [-1, 1] (bind_ann_base.lua.cc)
+    const float p0 = act == B200_ACT_LEAKY_RELU ? 0.01f : (act == B200_ACT_HARDTANH ? -1.0f : 0.0f);
+    const float p1 = act == B200_ACT_HARDTANH ? 1.0f : 0.0f;
+    return std::make_shared<ActivationFunctionANNComponent>(str(name), act, p0, p1);
+  });
+}
+b200_component *b200h_actf_new_ex(const char *kind, const char *name, float p0, float p1) {
+  return make([&] { return std::make_shared<ActivationFunctionANNComponent>(str(name), actfFromName(str(kind)), p0, p1); });
+}
+b200_component *b200h_prelu_new(const char *name, const char *weights, unsigned size, int scalar) {
+  return make([&] { return std::make_shared<PReLUActfANNComponent>(str(name), str(weights), size, scalar != 0); });
+}
+b200_component *b200h_dropout_new(const char *name, b200_random *random, float prob, float value, int norm, unsigned size) {
+  return make([&] {
+    if (!random) throw Error(B200_ERR_BAD_ARG, "dropout: a random object is mandatory");
+    return std::make_shared<DropoutANNComponent>(str(name), random->r, prob, value, norm != 0, size);
+  });
 }
 b200_component *b200h_rewrap_new(const char *name, const int *size, int ndims) {
   return make([&] { return std::make_shared<RewrapANNComponent>(str(name), std::vector<int>(size, size + ndims)); });
@@ -139,6 +162,9 @@ int b200h_trainer_randomize_weights(b200_trainer *t, b200_random *rnd, double in
 int b200h_trainer_set_flag(b200_trainer *t, const char *flag, int value) {
   API_TRY({
     std::string f = str(flag);
+    // every flag changes kernel arguments or the topology of the captured step graphs
+    t->t->invalidateGraphs();
+    if (f == "keep_gradients") t->t->sgd_dirty_public();
     if (f == "fuse") t->net->fuse = value != 0;
     else if (f == "cuda_graph") t->t->use_cuda_graph = value != 0;
     else if (f == "branches") t->t->use_branches = value != 0;
@@ -168,7 +194,12 @@ int b200h_trainer_weight_dims(b200_trainer *t, const char *name, int *dims2) {
   })
 }
 static MatrixPtr pick(b200_trainer *t, const char *name, int which) {
-  MatrixDict &d = which == 0 ? t->t->weights_table : (which == 1 ? t->t->grads : t->t->updates);
+  if (which < 0 || which > 4) throw Error(B200_ERR_BAD_ARG, "which: 0 weights, 1 gradients, 2 update, 3/4 optimizer state");
+  if (which >= 3) t->t->ensureOptimizerState();
+  MatrixDict &d = which == 0 ? t->t->weights_table
+                  : which == 1 ? t->t->grads
+                  : which == 2 ? t->t->updates
+                  : which == 3 ? t->t->state1 : t->t->state2;
   auto it = d.find(str(name));
   if (it == d.end()) throw Error(B200_ERR_BAD_ARG, "unknown weights name " + str(name));
   return it->second;
@@ -194,6 +225,27 @@ int b200h_trainer_train_step(b200_trainer *t, const float *x, const float *targe
     if (loss) *loss = l;
   })
 }
+int b200h_trainer_train_step_ex(b200_trainer *t, const float *x, const float *target, int bunch, int smoothing_bunch,
+                                double max_gradients_norm, float *loss, float *loss_rows) {
+  API_TRY({
+    if (max_gradients_norm < 0) throw Error(B200_ERR_BAD_ARG, "max_gradients_norm must be >= 0");
+    float l = t->t->trainStep(x, target, bunch, loss_rows, smoothing_bunch, max_gradients_norm);
+    if (loss) *loss = l;
+  })
+}
+int b200h_trainer_use_dataset(b200_trainer *t, const float *x, int n, float *y) { API_TRY(t->t->useDataset(x, n, y)) }
+int b200h_trainer_set_optimizer(b200_trainer *t, const char *name) {
+  API_TRY({
+    const std::string n = str(name);
+    const int k = n == "sgd" ? B200_OPT_SGD : n == "adagrad" ? B200_OPT_ADAGRAD : n == "rmsprop" ? B200_OPT_RMSPROP
+                  : n == "adadelta" ? B200_OPT_ADADELTA : -1;
+    if (k < 0) throw Error(B200_ERR_BAD_ARG, "unknown optimizer " + n + " (sgd, adagrad, rmsprop, adadelta)");
+    t->t->setOptimizer(k);
+  })
+}
+int b200h_trainer_get_count(b200_trainer *t, int64_t *count) { API_TRY(*count = t->t->getCount()) }
+int b200h_trainer_set_count(b200_trainer *t, int64_t count) { API_TRY(t->t->setCount(count)) }
+int b200h_trainer_set_loss_threshold(b200_trainer *t, float th) { API_TRY(t->t->loss.TH = th) }
 int b200h_trainer_validate_step(b200_trainer *t, const float *x, const float *target, int bunch, float *loss,
                                 float *loss_rows) {
   API_TRY({

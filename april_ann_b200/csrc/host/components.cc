@@ -2,6 +2,7 @@
 // component of the same name (packages/ann/ann/c_src/<name>_component.cc); the stack fuses
 // recognised runs into single launches.
 #include <math.h>
+#include <string.h>
 
 #include <exception>
 #include <sstream>
@@ -151,8 +152,10 @@ void BiasANNComponent::build(unsigned in, unsigned out, MatrixDict &weights, Com
 }
 
 // ------------------------------------------------------------------ activation functions
-ActivationFunctionANNComponent::ActivationFunctionANNComponent(const std::string &name, int act)
-    : ANNComponent(name, "", 0, 0), act(act) {}
+ActivationFunctionANNComponent::ActivationFunctionANNComponent(const std::string &name, int act, float p0, float p1)
+    : ANNComponent(name, "", 0, 0), act(act), p0(p0), p1(p1) {
+  if (act == B200_ACT_HARDTANH && !(p0 < p1)) throw Error(B200_ERR_BAD_ARG, "hardtanh: inf must be < sup [" + name + "]");
+}
 
 void ActivationFunctionANNComponent::build(unsigned in, unsigned out, MatrixDict &w, ComponentDict &c) {
   // activation_function_component.cc:150-166: input and output sizes are the same
@@ -168,6 +171,8 @@ MatrixPtr ActivationFunctionANNComponent::doForward(const MatrixPtr &in, bool) {
     check(b200_softmax_fwd(ctx, in->rows(), in->cols(), in->data, output->data));
   else if (act == B200_ACT_LOG_SOFTMAX)
     check(b200_log_softmax_fwd(ctx, in->rows(), in->cols(), in->data, output->data));
+  else if (act >= B200_ACT_LOG_LOGISTIC)
+    check(b200_actf_fwd_ex(ctx, act, p0, p1, in->size(), in->data, output->data));
   else
     check(b200_actf_fwd(ctx, act, in->size(), in->data, output->data));
   return output;
@@ -177,15 +182,19 @@ MatrixPtr ActivationFunctionANNComponent::doBackprop(const MatrixPtr &err) {
   if (err->size() != output->size())
     throw Error(129, "Different bunches found at doForward and doBackprop [" + name + "]");
   error_input = err;
-  if (act == B200_ACT_LOG_SOFTMAX) {
-    // log_softmax_actf_component.cc:44-52: the derivative is cancelled by the cross-entropy
-    // derivative; the reference copies, the copy is not needed on an immutable token.
+  if (act == B200_ACT_LOG_SOFTMAX || act == B200_ACT_LOG_LOGISTIC) {
+    // log_softmax_actf_component.cc:44-52, log_logistic_actf_component.cc:44-53: the derivative is
+    // cancelled by the cross-entropy derivative; the reference copies, the copy is not needed on an
+    // immutable token.
     error_output = err;
     return err;
   }
   error_output = Matrix::create(ctx, err->dims);
   if (act == B200_ACT_SOFTMAX)
     check(b200_softmax_bwd(ctx, err->rows(), err->cols(), output->data, err->data, error_output->data));
+  else if (act >= B200_ACT_LOG_LOGISTIC)
+    check(b200_actf_bwd_ex(ctx, act, p0, p1, err->size(), input ? input->data : nullptr, output->data, err->data,
+                           error_output->data));
   else
     check(b200_actf_bwd(ctx, act, err->size(), output->data, err->data, error_output->data));
   return error_output;
@@ -198,7 +207,112 @@ int actfFromName(const std::string &k) {
   if (k == "softmax") return B200_ACT_SOFTMAX;
   if (k == "log_softmax") return B200_ACT_LOG_SOFTMAX;
   if (k == "linear") return B200_ACT_LINEAR;
+  if (k == "log_logistic") return B200_ACT_LOG_LOGISTIC;
+  if (k == "softplus") return B200_ACT_SOFTPLUS;
+  if (k == "softsign") return B200_ACT_SOFTSIGN;
+  if (k == "leaky_relu") return B200_ACT_LEAKY_RELU;
+  if (k == "hardtanh") return B200_ACT_HARDTANH;
   throw Error(B200_ERR_BAD_ARG, "Incorrect component class: " + k);
+}
+
+// ------------------------------------------------------------------ prelu
+PReLUActfANNComponent::PReLUActfANNComponent(const std::string &name, const std::string &wname, unsigned size, bool scalar)
+    : ANNComponent(name, wname.empty() ? name : wname, size, size), scalar(scalar) {}
+void PReLUActfANNComponent::build(unsigned in, unsigned out, MatrixDict &weights, ComponentDict &components) {
+  if (input_size == 0) input_size = in ? in : out;
+  if (output_size == 0) output_size = input_size;
+  ANNComponent::build(in, out, weights, components);
+  if (input_size == 0) throw Error(256, "Unable to allocate prelu weights [" + name + "]");
+  const int wsize = scalar ? 1 : (int)input_size;
+  auto it = weights.find(weights_name);
+  if (it != weights.end()) {
+    weights_matrix = it->second;
+  } else {
+    if (!weights_matrix) weights_matrix = Matrix::create(ctx, std::vector<int>{wsize, 1});
+    weights[weights_name] = weights_matrix;
+  }
+  if ((int)weights_matrix->size() != wsize) throw Error(257, "Unexpected matrix size [" + name + "]");
+}
+MatrixPtr PReLUActfANNComponent::doForward(const MatrixPtr &in, bool) {
+  if (!weights_matrix) throw Error(B200_ERR_NOT_BUILT, "Not built component " + name);
+  if ((unsigned)in->cols() != input_size) throw Error(B200_ERR_BAD_ARG, "Incorrect input size [" + name + "]");
+  input = in;
+  output = Matrix::create(ctx, in->dims);
+  check(b200_prelu_fwd(ctx, in->rows(), in->cols(), in->data, weights_matrix->data, scalar ? 1 : 0, output->data));
+  return output;
+}
+MatrixPtr PReLUActfANNComponent::doBackprop(const MatrixPtr &err) {
+  if (!input) throw Error(B200_ERR_BAD_ARG, "backprop before forward [" + name + "]");
+  error_input = err;
+  error_output = Matrix::create(ctx, err->dims);
+  check(b200_prelu_bwd(ctx, input->rows(), input->cols(), input->data, weights_matrix->data, scalar ? 1 : 0, err->data,
+                       error_output->data));
+  return error_output;
+}
+void PReLUActfANNComponent::computeAllGradients(MatrixDict &grads) {
+  if (!input || !error_input) throw Error(B200_ERR_BAD_ARG, "computeGradients before forward/backprop [" + name + "]");
+  weights_matrix->shared_count += 1;
+  float beta;
+  MatrixPtr g = gradFor(grads, weights_name, weights_matrix, &beta);
+  MatrixPtr tmp = Matrix::create(ctx, input->dims);
+  check(b200_prelu_grad(ctx, input->rows(), input->cols(), input->data, error_input->data, scalar ? 1 : 0, grad_scale, beta,
+                        g->data, tmp->data));
+}
+void PReLUActfANNComponent::reset(unsigned it) {
+  ANNComponent::reset(it);
+  if (weights_matrix) weights_matrix->shared_count = 0;
+}
+
+// ------------------------------------------------------------------ dropout
+DropoutANNComponent::DropoutANNComponent(const std::string &name, const MTRand &random, float prob, float value, bool norm,
+                                         unsigned size)
+    : ANNComponent(name, "", size, size), random(random), prob(prob), value(value), normalize_after_training(norm) {}
+DropoutANNComponent::~DropoutANNComponent() {
+  if (mt_dev) b200_free(ctx, mt_dev);
+}
+void DropoutANNComponent::build(unsigned in, unsigned out, MatrixDict &w, ComponentDict &c) {
+  if (input_size == 0) input_size = in ? in : out;
+  if (output_size == 0) output_size = input_size;
+  ANNComponent::build(in, out, w, c);
+  if (input_size != output_size) throw Error(128, "Incorrect input/output sizes [" + name + "]");
+}
+MatrixPtr DropoutANNComponent::doForward(const MatrixPtr &in, bool during_training) {
+  input = in;
+  if (!(prob > 0.0f && (during_training || normalize_after_training))) {
+    output = in;   // dropout_component.cc:107-109
+    return output;
+  }
+  output = Matrix::create(ctx, in->dims);
+  if (during_training) {
+    if (!mt_dev) {
+      struct { uint32_t words[624]; int32_t next; int32_t pad[3]; } host;
+      memset(&host, 0, sizeof(host));
+      random.exportState(host.words, &host.next);
+      if (sizeof(host) != b200_mt_state_bytes()) throw Error(B200_ERR_BAD_ARG, "MT19937 state layout mismatch");
+      check(b200_malloc(ctx, &mt_dev, sizeof(host)));
+      check(b200_memcpy_h2d(ctx, mt_dev, &host, sizeof(host)));
+      check(b200_sync(ctx));
+    }
+    mask = Matrix::create(ctx, in->dims);
+    check(b200_dropout_mask(ctx, mt_dev, in->size(), prob, mask->data));
+    check(b200_mask_apply(ctx, in->size(), in->data, mask->data, value, output->data));
+  } else {
+    // matScal(output, 1 - prob): y = (1-prob) * x
+    check(b200_memcpy_d2d(ctx, output->data, in->data, in->size() * sizeof(float)));
+    check(b200_sscal(ctx, in->size(), 1.0f - prob, output->data));
+  }
+  return output;
+}
+MatrixPtr DropoutANNComponent::doBackprop(const MatrixPtr &err) {
+  error_input = err;
+  if (mask && prob > 0.0f) {
+    if (err->size() != mask->size()) throw Error(129, "Different bunches found at doForward and doBackprop [" + name + "]");
+    error_output = Matrix::create(ctx, err->dims);
+    check(b200_mask_apply(ctx, err->size(), err->data, mask->data, 0.0f, error_output->data));
+  } else {
+    error_output = err;
+  }
+  return error_output;
 }
 
 // ------------------------------------------------------------------ rewrap / flatten
@@ -339,32 +453,24 @@ MaxPoolingANNComponent::MaxPoolingANNComponent(const std::string &name, const st
     throw Error(B200_ERR_UNSUPPORTED, "max_pooling: only {1,kh,kw} kernels are supported");
   if (this->step.empty()) this->step = kernel;  // bind_ann_base.lua.cc:1485-1487
 }
-MaxPoolingANNComponent::~MaxPoolingANNComponent() {
-  if (argmax) b200_free(ctx, argmax);
-}
 MatrixPtr MaxPoolingANNComponent::doForward(const MatrixPtr &in, bool) {
   if (in->dims.size() != 4) throw Error(129, "Incorrect input matrix numDims [" + name + "]");
   input = in;
   const int B = in->dim(0), C = in->dim(1), H = in->dim(2), W = in->dim(3);
   const int oH = (H - kernel[1]) / step[1] + 1, oW = (W - kernel[2]) / step[2] + 1;
   output = Matrix::create(ctx, std::vector<int>{B, C, oH, oW});
-  const size_t need = output->size();
-  if (need > argmax_n) {
-    if (argmax) check(b200_free(ctx, argmax));
-    void *p;
-    check(b200_malloc(ctx, &p, need * sizeof(int32_t)));
-    argmax = (int32_t *)p;
-    argmax_n = need;
-  }
-  check(b200_maxpool_fwd(ctx, B, C, H, W, kernel[1], kernel[2], step[1], step[2], in->data, output->data, argmax));
+  argmax = Matrix::create(ctx, output->dims);   // 4-byte elements: holds the int32 positions
+  check(b200_maxpool_fwd(ctx, B, C, H, W, kernel[1], kernel[2], step[1], step[2], in->data, output->data,
+                         reinterpret_cast<int32_t *>(argmax->data)));
   return output;
 }
 MatrixPtr MaxPoolingANNComponent::doBackprop(const MatrixPtr &err) {
   error_input = err;
   const int B = input->dim(0), C = input->dim(1), H = input->dim(2), W = input->dim(3);
   error_output = Matrix::create(ctx, input->dims);
-  check(b200_maxpool_bwd(ctx, B, C, H, W, kernel[1], kernel[2], step[1], step[2], err->data, argmax,
-                         error_output->data));
+  if (!argmax) throw Error(B200_ERR_BAD_ARG, "backprop before forward [" + name + "]");
+  check(b200_maxpool_bwd(ctx, B, C, H, W, kernel[1], kernel[2], step[1], step[2], err->data,
+                         reinterpret_cast<const int32_t *>(argmax->data), error_output->data));
   return error_output;
 }
 void MaxPoolingANNComponent::reset(unsigned it) { ANNComponent::reset(it); }
@@ -413,7 +519,7 @@ MatrixPtr StackANNComponent::doForward(const MatrixPtr &in, bool during_training
   deferred_bias = nullptr;
   if (defer_last_actf) {
     auto *la = dynamic_cast<ActivationFunctionANNComponent *>(flat.back());
-    if (la && !la->elementwise()) {
+    if (la && la->rowwise()) {
       --n;  // the trainer runs it fused with the loss
       if (defer_output_layer && fuse && n >= 1) {
         size_t j = n;
@@ -644,7 +750,13 @@ std::shared_ptr<StackANNComponent> mlpAllAllGenerate(const std::string &topology
     const std::string &kind = tok[i + 1];
     std::string c = std::to_string(count);
     net->pushComponent(makeHyperplane("layer" + c, prev, size, "w" + c, "b" + c, "w" + c, "b" + c));
-    net->pushComponent(std::make_shared<ActivationFunctionANNComponent>("actf" + c, actfFromName(kind)));
+    {
+      // parameter defaults of the bindings: leaky_relu leak 0.01, hardtanh [-1, 1]
+      const int act = actfFromName(kind);
+      const float p0 = act == B200_ACT_LEAKY_RELU ? 0.01f : (act == B200_ACT_HARDTANH ? -1.0f : 0.0f);
+      const float p1 = act == B200_ACT_HARDTANH ? 1.0f : 0.0f;
+      net->pushComponent(std::make_shared<ActivationFunctionANNComponent>("actf" + c, act, p0, p1));
+    }
     prev = size;
     ++count;
   }

@@ -5,13 +5,17 @@
 // The whole train step (forward, loss, backward, weight gradients, [all-reduce], SGD, loss
 // statistics, step counter) is enqueued on one stream and, once warm, replayed as a CUDA graph.
 #include <cuda_runtime.h>
+#include <limits.h>
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
 
 #include "../../../include/b200ann_host.h"
 #include "ann.h"
+
+int b200_make_current(b200_ctx *ctx);   // runtime.cu: makes the context's device the current one
 
 namespace b200 {
 
@@ -42,6 +46,12 @@ void LossFunction::reset() { check(b200_memset_zero(ctx, stats_dev, 4 * sizeof(d
 
 static void checkLossArgs(const LossFunction &l, const MatrixPtr &in, const MatrixPtr &tg) {
   if (!in || !tg) throw Error(128, "Incorrect input token type, expected token matrix");
+  if (l.kind == LOSS_ZERO_ONE) {
+    // a dense target or a [bunch,1] vector of 1-based class labels (zero_one_loss_function.cc:82-118)
+    if (in->dims.size() != 2 || tg->rows() != in->rows() || (tg->cols() != in->cols() && tg->cols() != 1))
+      throw Error(128, "Incorrect target matrix bunch_size");
+    return;
+  }
   if (in->size() != tg->size()) throw Error(128, "Different token sizes found: input vs target");
   if (in->dims.size() != 2) throw Error(128, "loss input must be a 2-dimensional matrix");
   if (l.size != 0 && (unsigned)in->cols() != l.size) throw Error(128, "loss input size mismatch");
@@ -50,12 +60,14 @@ MatrixPtr LossFunction::computeLoss(const MatrixPtr &in, const MatrixPtr &tg) {
   checkLossArgs(*this, in, tg);
   MatrixPtr rows = Matrix::create(ctx, std::vector<int>{in->rows()});
   const int M = in->rows(), C = in->cols();
-  if (kind == LOSS_MSE) check(b200_mse_loss_grad(ctx, M, C, in->data, tg->data, rows->data, nullptr));
+  if (kind == LOSS_ZERO_ONE) check(b200_zero_one_loss(ctx, M, C, in->data, tg->data, tg->cols(), TH, rows->data));
+  else if (kind == LOSS_MSE) check(b200_mse_loss_grad(ctx, M, C, in->data, tg->data, rows->data, nullptr));
   else if (kind == LOSS_CROSS_ENTROPY) check(b200_ce_loss_grad(ctx, M, C, in->data, tg->data, rows->data, nullptr));
   else check(b200_mcce_loss_grad(ctx, M, C, in->data, tg->data, rows->data, nullptr));
   return rows;
 }
 MatrixPtr LossFunction::computeGradient(const MatrixPtr &in, const MatrixPtr &tg) {
+  if (kind == LOSS_ZERO_ONE) throw Error(128, "NON DIFERENTIABLE LOSS FUNCTION");   // zero_one_loss_function.cc:124-129
   checkLossArgs(*this, in, tg);
   MatrixPtr g = Matrix::create(ctx, in->dims);
   const int M = in->rows(), C = in->cols();
@@ -89,17 +101,26 @@ void LossFunction::getAccumLoss(float *mean, float *variance) {
 }
 
 // ------------------------------------------------------------------ optimizer options
-static const char *kSgdOptions[] = {"learning_rate", "momentum", "decay", "weight_decay", "L1_norm", "max_norm_penalty"};
-static bool validOption(const std::string &n) {
-  for (const char *o : kSgdOptions)
-    if (n == o) return true;
-  return false;
+SGDOptimizer::SGDOptimizer() { setKind(B200_OPT_SGD); }
+void SGDOptimizer::setKind(int k) {
+  kind = k;
+  layerwise_options.clear();
+  count = 0;
+  if (k == B200_OPT_SGD)   // optimizer_sgd.lua:39-47
+    global_options = {{"learning_rate", 0.01}, {"momentum", 0.0}, {"decay", 1e-05},
+                      {"weight_decay", 0.0},   {"L1_norm", 0.0},  {"max_norm_penalty", 0.0}};
+  else if (k == B200_OPT_ADAGRAD)   // optimizer_adagrad.lua:33-39
+    global_options = {{"learning_rate", 1.0}, {"decay", 0.95}, {"epsilon", 1e-06}, {"weight_decay", 0.0}, {"max_norm_penalty", 0.0}};
+  else if (k == B200_OPT_RMSPROP)   // optimizer_rmsprop.lua:35-42
+    global_options = {{"learning_rate", 0.01}, {"momentum", 0.0}, {"decay", 0.99}, {"epsilon", 1e-06},
+                      {"weight_decay", 0.0},   {"max_norm_penalty", 0.0}};
+  else if (k == B200_OPT_ADADELTA)  // optimizer_adadelta.lua:36-43
+    global_options = {{"learning_rate", 1.0}, {"momentum", 0.0}, {"decay", 0.95}, {"epsilon", 1e-06},
+                      {"weight_decay", 0.0},  {"max_norm_penalty", 0.0}};
+  else
+    throw Error(B200_ERR_BAD_ARG, "unknown optimizer");
 }
-SGDOptimizer::SGDOptimizer() {
-  // optimizer_sgd.lua:39-47
-  global_options = {{"learning_rate", 0.01}, {"momentum", 0.0}, {"decay", 1e-05},
-                    {"weight_decay", 0.0},   {"L1_norm", 0.0},  {"max_norm_penalty", 0.0}};
-}
+bool SGDOptimizer::validOption(const std::string &n) const { return global_options.count(n) != 0; }
 void SGDOptimizer::setOption(const std::string &n, double v) {
   if (!validOption(n)) throw Error(B200_ERR_BAD_ARG, "Not recognized option " + n);
   global_options[n] = v;
@@ -110,7 +131,8 @@ double SGDOptimizer::getOption(const std::string &n) const {
 }
 void SGDOptimizer::setLayerwiseOption(const std::string &layer, const std::string &n, double v) {
   if (!validOption(n)) throw Error(B200_ERR_BAD_ARG, "Not recognized option " + n);
-  if (n == "decay") throw Error(B200_ERR_BAD_ARG, "decay option cannot be defined layerwise, only globally");
+  if (n == "decay" && kind == B200_OPT_SGD)
+    throw Error(B200_ERR_BAD_ARG, "decay option cannot be defined layerwise, only globally");
   layerwise_options[layer][n] = v;
 }
 double SGDOptimizer::getOptionOf(const std::string &layer, const std::string &n) const {
@@ -166,6 +188,8 @@ SupervisedTrainer::~SupervisedTrainer() {
   if (count_dev) b200_free(ctx, count_dev);
   if (sgd_dev) b200_free(ctx, sgd_dev);
   if (sgd_light_dev) b200_free(ctx, sgd_light_dev);
+  if (opt_dev) b200_free(ctx, opt_dev);
+  if (norm_dev) b200_free(ctx, norm_dev);
   for (void *p : dp_imported) b200_ipc_close(ctx, p);
   if (dp_flags) b200_free(ctx, dp_flags);
   if (dp_recv) b200_free(ctx, dp_recv);
@@ -202,6 +226,12 @@ void SupervisedTrainer::build(unsigned input, unsigned output) {
     total += (discovered[n]->size() + 127) & ~size_t(127);
   }
   total_params = 0;
+  if (total > (size_t)INT32_MAX)
+    throw Error(B200_ERR_UNSUPPORTED, "models with more than 2^31-1 (padded) parameters are not supported by the flat arenas");
+  state1_arena.reset();
+  state2_arena.reset();
+  state1.clear();
+  state2.clear();
   weights_arena = Matrix::create(ctx, std::vector<int>{(int)total});
   grads_arena = Matrix::create(ctx, std::vector<int>{(int)total});
   updates_arena = Matrix::create(ctx, std::vector<int>{(int)total});
@@ -223,6 +253,15 @@ void SupervisedTrainer::build(unsigned input, unsigned output) {
   net->build(input, output, weights_table, comps2);
   loss.size = 0;
   sgd_dirty = true;
+  invalidateGraphs();
+}
+
+// Captured step graphs bake in everything that is a kernel ARGUMENT rather than device data: the
+// learning-rate decay, the gradient scale, the write-back flag, the graph topology (branches, fusion).
+// Whoever changes one of those drops the graphs; the next steps re-capture.
+void SupervisedTrainer::invalidateGraphs() {
+  if (graphs.empty()) return;
+  b200_sync(ctx);
   for (auto &kv : graphs) delete kv.second;
   graphs.clear();
 }
@@ -230,6 +269,33 @@ void SupervisedTrainer::build(unsigned input, unsigned output) {
 void SupervisedTrainer::setOption(const std::string &name, double v) {
   optimizer.setOption(name, v);
   sgd_dirty = true;
+  // the per-tensor hyper-parameters live in the device tables (re-uploaded before the next step), but
+  // SGD's global `decay` is passed to the update kernels by value
+  if (name == "decay" && optimizer.kind == B200_OPT_SGD) invalidateGraphs();
+}
+void SupervisedTrainer::setOptimizer(int kind) {
+  optimizer.setKind(kind);
+  sgd_dirty = true;
+  invalidateGraphs();
+  check(b200_memset_zero(ctx, count_dev, 2 * sizeof(int64_t)));
+  if (updates_arena) updates_arena->zeros();
+  state1_arena.reset();
+  state2_arena.reset();
+  state1.clear();
+  state2.clear();
+}
+int64_t SupervisedTrainer::getCount() {
+  int64_t c = 0;
+  check(b200_memcpy_d2h(ctx, &c, count_dev, sizeof(int64_t)));
+  check(b200_sync(ctx));
+  return c;
+}
+void SupervisedTrainer::setCount(int64_t c) {
+  int64_t v[2] = {c, 0};
+  check(b200_sync(ctx));
+  check(b200_memcpy_h2d(ctx, count_dev, v, 2 * sizeof(int64_t)));
+  check(b200_sync(ctx));
+  optimizer.count = c;
 }
 void SupervisedTrainer::setLayerwiseOption(const std::string &pattern, const std::string &name, double v) {
   // supervised.lua:262-269: the Lua pattern is expanded over the weight names
@@ -281,11 +347,47 @@ void SupervisedTrainer::uploadSgdTable() {
     t.n = weights_table[n]->size();
     t.rows = weights_table[n]->dim(0);
     t.cols = weights_table[n]->cols();
-    t.lr = (float)optimizer.getOptionOf(n, "learning_rate");
-    t.momentum = (float)optimizer.getOptionOf(n, "momentum");
-    t.weight_decay = (float)optimizer.getOptionOf(n, "weight_decay");
-    t.l1_norm = (float)optimizer.getOptionOf(n, "L1_norm");
-    t.max_norm_penalty = (float)optimizer.getOptionOf(n, "max_norm_penalty");
+    auto opt = [&](const char *o) { return optimizer.validOption(o) ? (float)optimizer.getOptionOf(n, o) : 0.0f; };
+    t.lr = opt("learning_rate");
+    t.momentum = opt("momentum");
+    t.weight_decay = opt("weight_decay");
+    t.l1_norm = opt("L1_norm");
+    t.max_norm_penalty = opt("max_norm_penalty");
+  }
+  if (optimizer.kind != B200_OPT_SGD) {
+    // adagrad / rmsprop / adadelta: arena-shaped state blocks, one generic table
+    const size_t total = weights_arena->size();
+    if (!state1_arena) {
+      state1_arena = Matrix::create(ctx, std::vector<int>{(int)total});
+      state1_arena->zeros();
+      state2_arena = Matrix::create(ctx, std::vector<int>{(int)total});
+      state2_arena->zeros();
+      for (auto &n : weights_order) {
+        const size_t off = (size_t)(weights_table[n]->data - weights_arena->data);
+        state1[n] = Matrix::view(state1_arena, off, weights_table[n]->dims);
+        state2[n] = Matrix::view(state2_arena, off, weights_table[n]->dims);
+      }
+    }
+    opt_host.resize(nt);
+    for (int i = 0; i < nt; ++i) {
+      const std::string &n = arena_order[i];
+      b200_opt_tensor &o = opt_host[i];
+      memset(&o, 0, sizeof(o));
+      o.w = sgd_host[i].w; o.g = sgd_host[i].g; o.u = sgd_host[i].u;
+      o.s1 = state1[n]->data; o.s2 = state2[n]->data;
+      o.n = sgd_host[i].n; o.rows = sgd_host[i].rows; o.cols = sgd_host[i].cols;
+      o.lr = sgd_host[i].lr; o.momentum = sgd_host[i].momentum;
+      o.decay = (float)optimizer.getOptionOf(n, "decay");
+      o.epsilon = (float)optimizer.getOptionOf(n, "epsilon");
+      o.weight_decay = sgd_host[i].weight_decay; o.max_norm_penalty = sgd_host[i].max_norm_penalty;
+      o.write_back_grad = keep_gradients ? 1 : 0;
+    }
+    if (!opt_dev) {
+      void *p;
+      check(b200_malloc(ctx, &p, sizeof(b200_opt_tensor) * (size_t)std::max(nt, 1)));
+      opt_dev = (b200_opt_tensor *)p;
+    }
+    check(b200_memcpy_h2d(ctx, opt_dev, opt_host.data(), sizeof(b200_opt_tensor) * (size_t)nt));
   }
   if (!sgd_dev) {
     void *p;
@@ -319,9 +421,9 @@ void SupervisedTrainer::uploadSgdTable() {
   // are part of the graph structure: re-capture when that set changes
   std::string sig;
   for (auto &t : sgd_host) sig += (t.max_norm_penalty > 0.0f) ? '1' : '0';
+  for (auto &t : sgd_host) sig += (t.momentum > 0.0f) ? 'm' : '-';   // rmsprop's look-ahead launch exists only with momentum
   if (sig != sgd_signature) {
-    for (auto &kv : graphs) delete kv.second;
-    graphs.clear();
+    invalidateGraphs();
     sgd_signature = sig;
   }
 }
@@ -364,7 +466,66 @@ MatrixPtr SupervisedTrainer::outputLayerFused(const MatrixPtr &h, const MatrixPt
 }
 
 // One training step enqueued on the stream: supervised.lua:769-819 + optimizer_sgd.lua:50-100.
-void SupervisedTrainer::runStep(const MatrixPtr &x, const MatrixPtr &t, int global_bunch) {
+// Bucket plan of the fused replica-group update, in arena order (= the order in which the backward pass
+// finishes gradients).  b200_dp_fused_update takes at most 32 tensors per launch and the tag block has 16
+// bucket slots; when a net of very many small tensors cannot be cut that way the caller stays on the
+// NCCL all-reduce path, which has no such limits.
+bool SupervisedTrainer::dpBucketPlan(std::vector<std::pair<int, int>> *out) {
+  const int nt = (int)arena_order.size();
+  size_t threshold = dp_bucket_bytes ? dp_bucket_bytes : 1;
+  for (int attempt = 0; attempt < 32; ++attempt, threshold *= 2) {
+    std::vector<std::pair<int, int>> plan;
+    int lo = 0;
+    size_t bytes = 0;
+    for (int i = 0; i < nt; ++i) {
+      bytes += grads[arena_order[i]]->size() * sizeof(float);
+      if (bytes >= threshold || i + 1 - lo == 32 || i == nt - 1) {
+        plan.emplace_back(lo, i + 1);
+        lo = i + 1;
+        bytes = 0;
+      }
+    }
+    if (plan.size() <= 16) {
+      if (out) *out = plan;
+      return true;
+    }
+    if (nt > 16 * 32) break;
+  }
+  return false;
+}
+
+// The update of a step as ONE launch over every tensor once every gradient exists: the path of the
+// optimizers other than SGD, and of SGD when the global gradient norm is clipped (the clip needs every
+// gradient before the first update).  Replica groups all-reduce the whole gradient arena first.
+void SupervisedTrainer::runUpdateSimple(double max_gradients_norm) {
+  const int nt = (int)arena_order.size();
+  check(b200_branch_join_all(ctx));
+  if (dp_nranks > 1) {
+    check(b200_allreduce_sum_async(ctx, grads_arena->data, grads_arena->size(), 0));
+    check(b200_comm_wait(ctx, 0));
+  }
+  if (max_gradients_norm > 0.0) {
+    if (!norm_dev) {
+      void *p;
+      check(b200_malloc(ctx, &p, 512));
+      norm_dev = (float *)p;
+    }
+    check(b200_grad_clip(ctx, grads_arena->size(), grads_arena->data, (float)max_gradients_norm, norm_dev));
+  }
+  if (optimizer.kind == B200_OPT_SGD) {
+    const int wb = keep_gradients ? B200_SGD_WRITE_BACK_GRAD : 0;
+    check(b200_sgd_multi_tensor_ex(ctx, nt, sgd_dev, sgd_host.data(), optimizer.getOption("decay"), count_dev,
+                                   wb | B200_SGD_INCREMENT_COUNT));
+  } else {
+    check(b200_optimizer_multi_tensor(ctx, optimizer.kind, nt, opt_dev, opt_host.data(), count_dev, 1));
+  }
+}
+
+void SupervisedTrainer::runStep(const MatrixPtr &x, const MatrixPtr &t, int global_bunch, double max_gradients_norm) {
+  if (loss.kind == LOSS_ZERO_ONE) throw Error(128, "NON DIFERENTIABLE LOSS FUNCTION");
+  // rmsprop evaluates the gradient at the look-ahead point w - momentum*Eupdate (optimizer_rmsprop.lua:44-51)
+  if (optimizer.kind == B200_OPT_RMSPROP)
+    check(b200_optimizer_lookahead(ctx, (int)opt_host.size(), opt_dev, opt_host.data()));
   net->reset();
   for (auto &kv : grads) kv.second->fresh = true;
   auto *last = dynamic_cast<ActivationFunctionANNComponent *>(net->lastComponent());
@@ -426,13 +587,31 @@ void SupervisedTrainer::runStep(const MatrixPtr &x, const MatrixPtr &t, int glob
   };
   bool any_max_norm = false;
   for (auto &t : sgd_host) any_max_norm = any_max_norm || t.max_norm_penalty > 0.0f;
-  if (dp_nranks > 1 && dp_fused && !keep_gradients && !any_max_norm) {
+  if (optimizer.kind != B200_OPT_SGD || max_gradients_norm > 0.0) {
+    net->use_branches = use_branches;
+    if (use_branches) check(b200_branch_begin(ctx, 0));
+    loss.accumLoss(rows);
+    if (use_branches) check(b200_branch_end(ctx));
+    try {
+      net->doBackprop(grad);
+      cleanup();
+      runUpdateSimple(max_gradients_norm);
+    } catch (...) {
+      cleanup();
+      b200_branch_join_all(ctx);
+      throw;
+    }
+  } else if (dp_nranks > 1 && dp_fused && !keep_gradients && !any_max_norm && dpBucketPlan(nullptr)) {
     // Replica group over NVLink peer memory: one kernel per bucket reduces the peers' gradient shards, updates
     // this rank's shard and writes the new weights into every replica (b200_dp_fused_update).  A bucket is
     // launched once its gradients are final AND the data gradients that read its weights have been issued
     // (the peers will overwrite them), on branch 0 beside the contractions still to come; the last bucket
     // on the main stream after the join.  b200_dp_wait then holds the step until every shard has landed.
-    int next = 0, nbuckets = 0;
+    // buckets are planned up front (dpBucketPlan): at least dp_bucket_bytes of gradients each, at most 32
+    // tensors (the kernel's shared tables) and at most 16 buckets (the tag block)
+    std::vector<std::pair<int, int>> plan;
+    dpBucketPlan(&plan);
+    int nextb = 0, nbuckets = 0;
     auto launchBucket = [&](int lo, int hi, bool last) {
       if (last) {
         check(b200_branch_join_all(ctx));
@@ -450,14 +629,15 @@ void SupervisedTrainer::runStep(const MatrixPtr &x, const MatrixPtr &t, int glob
       ++nbuckets;
     };
     auto flush = [&](bool force) {
-      int hi = next;
-      size_t bytes = 0;
-      while (hi < nt && done[hi]) { bytes += grads[arena_order[hi]]->size() * sizeof(float); ++hi; }
-      if (hi == next) return;
-      if (!force && bytes < dp_bucket_bytes && hi < nt) return;
-      if (nbuckets >= 15 && hi < nt) return;   // keep one slot for the tail
-      launchBucket(next, hi, force || hi == nt);
-      next = hi;
+      while (nextb < (int)plan.size()) {
+        bool ready = true;
+        for (int i = plan[nextb].first; i < plan[nextb].second; ++i) ready = ready && done[i];
+        if (!ready) break;
+        const bool last = nextb + 1 == (int)plan.size();
+        if (last && !force) break;   // the last bucket goes on the main stream, after the join
+        launchBucket(plan[nextb].first, plan[nextb].second, last);
+        ++nextb;
+      }
     };
     net->use_branches = use_branches;
     net->on_backprop_issued = [&](ANNComponent *c, int) {
@@ -624,18 +804,27 @@ void SupervisedTrainer::runStep(const MatrixPtr &x, const MatrixPtr &t, int glob
   last_output = out;
 }
 
-void SupervisedTrainer::trainStepDevice(const MatrixPtr &x, const MatrixPtr &t) {
+void SupervisedTrainer::trainStepDevice(const MatrixPtr &x, const MatrixPtr &t, int smoothing_bunch,
+                                        double max_gradients_norm) {
   if (weights_order.empty()) throw Error(B200_ERR_NOT_BUILT, "Execute build method before call this method");
+  check(b200_make_current(ctx));
   if (sgd_dirty) {
     // hyper-parameters are baked into the SGD table; captured graphs read it from the device
     uploadSgdTable();
   }
   const int bunch = x->rows();
-  const int global_bunch = bunch * dp_nranks;
+  // supervised.lua:757,800: the smoothing factor uses `bunch_size or self.bunch_size or 1`, NOT the row count
+  // of the bunch (train_dataset passes the actual length of every bunch, supervised.lua:1203)
+  if (smoothing_bunch <= 0) smoothing_bunch = bunch_size > 0 ? bunch_size : 1;
+  const int global_bunch = smoothing_bunch * dp_nranks;
+  if (max_gradients_norm != graph_max_norm) {   // the clip threshold is a kernel argument of the captured step
+    invalidateGraphs();
+    graph_max_norm = max_gradients_norm;
+  }
   cudaStream_t stream = (cudaStream_t)b200_stream(ctx);
   Graph *g = nullptr;
   if (use_cuda_graph) {
-    const auto key = std::make_pair(bunch, (const float *)x->data);
+    const auto key = std::make_pair(std::make_pair(bunch, smoothing_bunch), (const float *)x->data);
     auto it = graphs.find(key);
     if (it == graphs.end()) {
       if (graphs.size() >= 16) {   // callers that feed ever-changing buffers: do not hoard graphs
@@ -664,7 +853,7 @@ void SupervisedTrainer::trainStepDevice(const MatrixPtr &x, const MatrixPtr &t) 
     g_capture_registry = &g->keep;
     cudaCheck(cudaStreamBeginCapture(stream, cudaStreamCaptureModeRelaxed), "cudaStreamBeginCapture");
     try {
-      runStep(x, t, global_bunch);
+      runStep(x, t, global_bunch, max_gradients_norm);
     } catch (...) {
       g_capture_registry = nullptr;
       cudaGraph_t dead = nullptr;
@@ -687,7 +876,7 @@ void SupervisedTrainer::trainStepDevice(const MatrixPtr &x, const MatrixPtr &t) 
     optimizer.count++;
     return;
   }
-  runStep(x, t, global_bunch);
+  runStep(x, t, global_bunch, max_gradients_norm);
   if (g) g->warm++;
   optimizer.count++;
 }
@@ -726,18 +915,20 @@ MatrixPtr SupervisedTrainer::calculate(const MatrixPtr &x) {
 
 static MatrixPtr stageView(b200_ctx *ctx, MatrixPtr &stage, int rows, int cols, int min_rows) {
   const size_t need = (size_t)std::max(rows, min_rows) * cols;
+  if (need > (size_t)INT32_MAX) throw Error(B200_ERR_UNSUPPORTED, "bunch of more than 2^31-1 values");
   if (!stage || stage->size() < need) stage = Matrix::create(ctx, std::vector<int>{(int)need});
   return Matrix::view(stage, 0, std::vector<int>{rows, cols});
 }
 
-float SupervisedTrainer::trainStep(const float *x, const float *t, int bunch, float *loss_rows_out) {
+float SupervisedTrainer::trainStep(const float *x, const float *t, int bunch, float *loss_rows_out, int smoothing_bunch,
+                                   double max_gradients_norm) {
   const int in = (int)net->getInputSize(), out = (int)net->getOutputSize();
   if (in <= 0 || out <= 0) throw Error(B200_ERR_NOT_BUILT, "Execute build method before call this method");
   MatrixPtr sx = stageView(ctx, stage_x, bunch, in, bunch_size);
   MatrixPtr st = stageView(ctx, stage_t, bunch, out, bunch_size);
   sx->fromHost(x);
   st->fromHost(t);
-  trainStepDevice(sx, st);
+  trainStepDevice(sx, st, smoothing_bunch, max_gradients_norm);
   std::vector<float> rows(bunch);
   last_loss_rows->toHost(rows.data());
   if (loss_rows_out) memcpy(loss_rows_out, rows.data(), sizeof(float) * bunch);
@@ -783,7 +974,7 @@ void SupervisedTrainer::trainDataset(const float *x, const float *t, int n, cons
     MatrixPtr st = stageView(ctx, stage_t, b, out, bunch_size);
     check(b200_gather_rows(ctx, b, in, dx->data, idx_dev + k, sx->data));
     check(b200_gather_rows(ctx, b, out, dt->data, idx_dev + k, st->data));
-    trainStepDevice(sx, st);
+    trainStepDevice(sx, st, b);   // #bunch_indexes, supervised.lua:1203
   }
   loss.getAccumLoss(mean, var);  // also synchronises: idx / dataset buffers are idle afterwards
   check(b200_free(ctx, idx_dev));
@@ -802,6 +993,22 @@ void SupervisedTrainer::validateDataset(const float *x, const float *t, int n, f
                        Matrix::view(dt, (size_t)k * out, std::vector<int>{b, out}));
   }
   loss.getAccumLoss(mean, var);
+}
+
+void SupervisedTrainer::useDataset(const float *x, int n, float *y) {
+  // supervised.lua:1291-1430: forward (not training) bunch by bunch, outputs collected on the host
+  const int in = (int)net->getInputSize(), out = (int)net->getOutputSize();
+  if (in <= 0 || out <= 0) throw Error(B200_ERR_NOT_BUILT, "Execute build method before call this method");
+  MatrixPtr dx = Matrix::create(ctx, std::vector<int>{n, in});
+  dx->fromHost(x);
+  MatrixPtr dy = Matrix::create(ctx, std::vector<int>{n, out});
+  for (int k = 0; k < n; k += bunch_size) {
+    const int b = std::min(bunch_size, n - k);
+    MatrixPtr o = calculate(Matrix::view(dx, (size_t)k * in, std::vector<int>{b, in}));
+    if ((int)o->size() != b * out) throw Error(B200_ERR_BAD_ARG, "use_dataset: unexpected output size");
+    check(b200_memcpy_d2d(ctx, dy->data + (size_t)k * out, o->data, sizeof(float) * (size_t)b * out));
+  }
+  dy->toHost(y);
 }
 
 double SupervisedTrainer::norm2(const std::string &pattern) {
@@ -869,8 +1076,7 @@ void SupervisedTrainer::dpConnect(int nranks, int rank, const unsigned char *all
   }
   dp_fused = true;
   if (const char *e = getenv("B200_DP_FUSED")) dp_fused = atoi(e) != 0;
-  for (auto &kv : graphs) delete kv.second;
-  graphs.clear();
+  invalidateGraphs();
 }
 
 float SupervisedTrainer::dpBench(int reps) {
@@ -913,6 +1119,7 @@ namespace b200 {
 void SupervisedTrainer::stage(const float *x, const float *t, int bunch) {
   const int in = (int)net->getInputSize(), out = (int)net->getOutputSize();
   if (in <= 0 || out <= 0) throw Error(B200_ERR_NOT_BUILT, "Execute build method before call this method");
+  check(b200_make_current(ctx));
   if (!copy_stream) {
     cudaStream_t cs;
     cudaCheck(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking), "cudaStreamCreate");
@@ -942,7 +1149,7 @@ void SupervisedTrainer::stepStaged(int bunch) {
   const int s = staged_slot;
   cudaStream_t stream = (cudaStream_t)b200_stream(ctx);
   cudaCheck(cudaStreamWaitEvent(stream, (cudaEvent_t)ev_copied[s], 0), "cudaStreamWaitEvent");
-  trainStepDevice(stageView(ctx, pipe_x[s], bunch, in, bunch_size), stageView(ctx, pipe_t[s], bunch, out, bunch_size));
+  trainStepDevice(stageView(ctx, pipe_x[s], bunch, in, bunch_size), stageView(ctx, pipe_t[s], bunch, out, bunch_size), bunch);
   cudaCheck(cudaEventRecord((cudaEvent_t)ev_trained[s], stream), "cudaEventRecord");
   slot_trained[s] = true;
 }

@@ -99,6 +99,7 @@ extern "C" int b200_comm_unique_id(void *id128) {
 }
 
 extern "C" int b200_comm_init(b200_ctx *ctx, int nranks, int rank, const void *id128) {
+  B200_ENTER(ctx);
   ARG_CHECK(ctx && id128, "NULL pointer");
   ARG_CHECK(nranks >= 1 && rank >= 0 && rank < nranks, "bad rank");
   NcclApi *a = nccl();
@@ -116,6 +117,7 @@ extern "C" int b200_comm_init(b200_ctx *ctx, int nranks, int rank, const void *i
 }
 
 extern "C" int b200_comm_destroy(b200_ctx *ctx) {
+  B200_ENTER(ctx);
   if (!ctx || !ctx->nccl_comm) return B200_OK;
   NcclApi *a = nccl();
   if (a && a->CommDestroy) a->CommDestroy((ncclComm_t)ctx->nccl_comm);
@@ -140,6 +142,7 @@ static int allreduce_impl(b200_ctx *ctx, void *buf, size_t n, int dtype) {
   return B200_OK;
 }
 extern "C" int b200_allreduce_sum_async(b200_ctx *ctx, float *buf, size_t n, int slot) {
+  B200_ENTER(ctx);
   ARG_CHECK(ctx && buf, "NULL pointer");
   ARG_CHECK(slot >= 0 && slot < 16, "slot out of range");
   if (ctx->nranks <= 1 || n == 0) return B200_OK;
@@ -156,17 +159,21 @@ extern "C" int b200_allreduce_sum_async(b200_ctx *ctx, float *buf, size_t n, int
   return B200_OK;
 }
 extern "C" int b200_comm_wait(b200_ctx *ctx, int slot) {
+  B200_ENTER(ctx);
   ARG_CHECK(ctx, "NULL pointer");
   ARG_CHECK(slot >= 0 && slot < 16, "slot out of range");
   if (ctx->nranks <= 1) return B200_OK;
   CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_bucket[slot], 0));
   return B200_OK;
 }
-extern "C" int b200_allreduce_sum(b200_ctx *ctx, float *buf, size_t n) { return allreduce_impl(ctx, buf, n, ncclFloat32); }
+extern "C" int b200_allreduce_sum(b200_ctx *ctx, float *buf, size_t n) {
+  B200_ENTER(ctx); return allreduce_impl(ctx, buf, n, ncclFloat32); }
 extern "C" int b200_allreduce_sum_f64(b200_ctx *ctx, double *buf, size_t n) {
+  B200_ENTER(ctx);
   return allreduce_impl(ctx, buf, n, ncclFloat64);
 }
 extern "C" int b200_broadcast(b200_ctx *ctx, float *buf, size_t n, int root) {
+  B200_ENTER(ctx);
   ARG_CHECK(ctx && buf, "NULL pointer");
   if (ctx->nranks <= 1 || n == 0) return B200_OK;
   ARG_CHECK(ctx->nccl_comm, "communicator not initialised (b200_comm_init)");

@@ -265,34 +265,40 @@ int launch_rows(b200_ctx *ctx, int M, int C, const RowArgs &p) {
 }  // namespace
 
 extern "C" int b200_softmax_fwd(b200_ctx *ctx, int M, int C, const float *x, float *y) {
+  B200_ENTER(ctx);
   ARG_CHECK(ctx && x && y, "NULL pointer");
   RowArgs p{x, nullptr, y, nullptr, nullptr};
   return launch_rows<OP_SOFTMAX>(ctx, M, C, p);
 }
 extern "C" int b200_log_softmax_fwd(b200_ctx *ctx, int M, int C, const float *x, float *y) {
+  B200_ENTER(ctx);
   ARG_CHECK(ctx && x && y, "NULL pointer");
   RowArgs p{x, nullptr, y, nullptr, nullptr};
   return launch_rows<OP_LOG_SOFTMAX>(ctx, M, C, p);
 }
 extern "C" int b200_softmax_bwd(b200_ctx *ctx, int M, int C, const float *y, const float *dy, float *dx) {
+  B200_ENTER(ctx);
   ARG_CHECK(ctx && y && dy && dx, "NULL pointer");
   RowArgs p{y, dy, dx, nullptr, nullptr};
   return launch_rows<OP_SOFTMAX_BWD>(ctx, M, C, p);
 }
 extern "C" int b200_mcce_loss_grad(b200_ctx *ctx, int M, int C, const float *logp, const float *target,
                                    float *loss_rows, float *grad) {
+  B200_ENTER(ctx);
   ARG_CHECK(ctx && logp && target, "NULL pointer");
   RowArgs p{logp, target, grad, nullptr, loss_rows};
   return launch_rows<OP_MCCE>(ctx, M, C, p);
 }
 extern "C" int b200_mse_loss_grad(b200_ctx *ctx, int M, int C, const float *out, const float *target,
                                   float *loss_rows, float *grad) {
+  B200_ENTER(ctx);
   ARG_CHECK(ctx && out && target, "NULL pointer");
   RowArgs p{out, target, grad, nullptr, loss_rows};
   return launch_rows<OP_MSE>(ctx, M, C, p);
 }
 extern "C" int b200_ce_loss_grad(b200_ctx *ctx, int M, int C, const float *log_out, const float *target,
                                  float *loss_rows, float *grad) {
+  B200_ENTER(ctx);
   ARG_CHECK(ctx && log_out && target, "NULL pointer");
   RowArgs p{log_out, target, grad, nullptr, loss_rows};
   return launch_rows<OP_CE>(ctx, M, C, p);
@@ -300,6 +306,7 @@ extern "C" int b200_ce_loss_grad(b200_ctx *ctx, int M, int C, const float *log_o
 extern "C" int b200_log_softmax_mcce_fused(b200_ctx *ctx, int M, int C, const float *logits,
                                            const float *target, float *logp, float *loss_rows,
                                            float *grad) {
+  B200_ENTER(ctx);
   ARG_CHECK(ctx && logits && target, "NULL pointer");
   RowArgs p{logits, target, logp, grad, loss_rows};
   return launch_rows<OP_LSM_MCCE>(ctx, M, C, p);

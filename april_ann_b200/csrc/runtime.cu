@@ -23,6 +23,14 @@ int b200_check_cuda(cudaError_t e, const char *what, const char *file, int line)
 
 extern "C" const char *b200_last_error_string(void) { return g_err; }
 
+// One host thread may drive several contexts (devices): launches, allocations and function attributes
+// apply to the CURRENT device, so every entry point switches to its context's device when it differs.
+int b200_make_current(b200_ctx *ctx) {
+  int cur = -1;
+  if (cudaGetDevice(&cur) == cudaSuccess && cur == ctx->device) return B200_OK;
+  return b200_check_cuda(cudaSetDevice(ctx->device), "cudaSetDevice", __FILE__, __LINE__);
+}
+
 extern "C" int b200_device_count(int *count) {
   ARG_CHECK(count, "count is NULL");
   cudaError_t e = cudaGetDeviceCount(count);
@@ -76,6 +84,7 @@ extern "C" int b200_create(int device, b200_ctx **out) {
 }
 
 extern "C" int b200_pool_trim(b200_ctx *ctx) {
+  B200_ENTER(ctx);
   ARG_CHECK(ctx, "ctx is NULL");
   std::lock_guard<std::mutex> lk(ctx->mu);
   CUDA_TRY(cudaSetDevice(ctx->device));
@@ -88,6 +97,7 @@ extern "C" int b200_pool_trim(b200_ctx *ctx) {
 extern "C" int b200_comm_destroy(b200_ctx *ctx);
 
 extern "C" int b200_destroy(b200_ctx *ctx) {
+  B200_ENTER(ctx);
   if (!ctx) return B200_OK;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
@@ -96,6 +106,7 @@ extern "C" int b200_destroy(b200_ctx *ctx) {
   b200_pool_trim(ctx);
   for (auto &kv : ctx->live_blocks) cudaFree(kv.first);
   for (auto &p : ctx->scratch) if (p) cudaFree(p);
+  for (void *p : ctx->retired_scratch) cudaFree(p);
   for (auto &kv : ctx->deferred_free) cudaFree(kv.second);
   for (int i = 0; i < b200_ctx::kBranches; ++i) {
     cudaEventDestroy(ctx->ev_fork[i]);
@@ -112,17 +123,20 @@ extern "C" int b200_destroy(b200_ctx *ctx) {
 }
 
 extern "C" int b200_set_math_mode(b200_ctx *ctx, int mode) {
+  B200_ENTER(ctx);
   ARG_CHECK(ctx, "ctx is NULL");
   ARG_CHECK(mode == B200_MATH_FP32 || mode == B200_MATH_TF32, "unknown math mode");
   ctx->math_mode = mode;
   return B200_OK;
 }
 extern "C" int b200_get_math_mode(b200_ctx *ctx, int *mode) {
+  B200_ENTER(ctx);
   ARG_CHECK(ctx && mode, "NULL");
   *mode = ctx->math_mode;
   return B200_OK;
 }
 extern "C" int b200_sm_count(b200_ctx *ctx, int *count) {
+  B200_ENTER(ctx);
   ARG_CHECK(ctx && count, "NULL");
   *count = ctx->sm_count;
   return B200_OK;
@@ -130,6 +144,7 @@ extern "C" int b200_sm_count(b200_ctx *ctx, int *count) {
 extern "C" void *b200_stream(b200_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 
 extern "C" int b200_sync(b200_ctx *ctx) {
+  B200_ENTER(ctx);
   ARG_CHECK(ctx, "ctx is NULL");
   CUDA_TRY(cudaStreamSynchronize(ctx->main_stream));
   for (int i = 0; i < b200_ctx::kBranches; ++i) CUDA_TRY(cudaStreamSynchronize(ctx->side_stream[i]));
@@ -143,6 +158,7 @@ extern "C" int b200_sync(b200_ctx *ctx) {
 // side stream i holds.  b200_branch_join_all: the main stream waits for every open branch.  Inside
 // a stream capture these calls become the fork / join edges of the graph.
 extern "C" int b200_branch_begin(b200_ctx *ctx, int branch) {
+  B200_ENTER(ctx);
   ARG_CHECK(ctx, "ctx is NULL");
   ARG_CHECK(branch >= 0 && branch < b200_ctx::kBranches, "no such branch");
   ARG_CHECK(ctx->cur_branch < 0, "branches do not nest");
@@ -154,12 +170,14 @@ extern "C" int b200_branch_begin(b200_ctx *ctx, int branch) {
   return B200_OK;
 }
 extern "C" int b200_branch_end(b200_ctx *ctx) {
+  B200_ENTER(ctx);
   ARG_CHECK(ctx, "ctx is NULL");
   ctx->cur_branch = -1;
   ctx->stream = ctx->main_stream;
   return B200_OK;
 }
 extern "C" int b200_branch_wait(b200_ctx *ctx, int branch) {
+  B200_ENTER(ctx);
   ARG_CHECK(ctx, "ctx is NULL");
   ARG_CHECK(branch >= 0 && branch < b200_ctx::kBranches, "no such branch");
   if (!ctx->side_open[branch] || ctx->cur_branch == branch) return B200_OK;
@@ -168,6 +186,7 @@ extern "C" int b200_branch_wait(b200_ctx *ctx, int branch) {
   return B200_OK;
 }
 extern "C" int b200_branch_join_all(b200_ctx *ctx) {
+  B200_ENTER(ctx);
   ARG_CHECK(ctx, "ctx is NULL");
   ctx->cur_branch = -1;
   ctx->stream = ctx->main_stream;
@@ -183,6 +202,7 @@ extern "C" int b200_branch_join_all(b200_ctx *ctx) {
   return B200_OK;
 }
 extern "C" int b200_set_sm_budget(b200_ctx *ctx, int sms) {
+  B200_ENTER(ctx);
   ARG_CHECK(ctx, "ctx is NULL");
   ctx->sm_budget = (sms > 0 && sms < ctx->sm_count) ? sms : 0;
   return B200_OK;
@@ -195,6 +215,7 @@ static size_t round_size(size_t bytes) {
 }
 
 extern "C" int b200_malloc(b200_ctx *ctx, void **dptr, size_t bytes) {
+  B200_ENTER(ctx);
   ARG_CHECK(ctx && dptr, "NULL");
   size_t sz = round_size(bytes ? bytes : 1);
   std::lock_guard<std::mutex> lk(ctx->mu);
@@ -227,6 +248,7 @@ extern "C" int b200_malloc(b200_ctx *ctx, void **dptr, size_t bytes) {
 }
 
 extern "C" int b200_free(b200_ctx *ctx, void *dptr) {
+  B200_ENTER(ctx);
   ARG_CHECK(ctx, "ctx is NULL");
   if (!dptr) return B200_OK;
   std::lock_guard<std::mutex> lk(ctx->mu);
@@ -244,10 +266,12 @@ extern "C" int b200_free(b200_ctx *ctx, void *dptr) {
 void *b200_scratch(b200_ctx *ctx, size_t bytes) {
   const int slot = ctx->cur_branch + 1;
   if (bytes <= ctx->scratch_bytes[slot]) return ctx->scratch[slot];
-  // growing the scratch must not race with kernels still using the old one (never happens inside a
-  // capture: the eager warm-up steps have sized every branch's scratch)
-  cudaStreamSynchronize(ctx->stream);
-  if (ctx->scratch[slot]) cudaFree(ctx->scratch[slot]);
+  // Growing the scratch: kernels in flight and, above all, already CAPTURED graphs (split reductions, column
+  // sums, convolution weight gradients) hold the old pointer, and graphs are cached per bunch size -- a small
+  // bunch captured first, a larger one afterwards, then the first graph replayed.  The old block is therefore
+  // retired, not freed: it stays allocated until b200_destroy.  (Scratch blocks are small and grow
+  // geometrically in practice: a handful of retired blocks per context.)
+  if (ctx->scratch[slot]) ctx->retired_scratch.push_back(ctx->scratch[slot]);
   size_t sz = round_size(bytes);
   if (cudaMalloc(&ctx->scratch[slot], sz) != cudaSuccess) {
     ctx->scratch[slot] = nullptr;
@@ -269,21 +293,25 @@ extern "C" int b200_host_free(void *hptr) {
   return B200_OK;
 }
 extern "C" int b200_memcpy_h2d(b200_ctx *ctx, void *dst, const void *src, size_t bytes) {
+  B200_ENTER(ctx);
   ARG_CHECK(ctx, "ctx is NULL");
   if (bytes) CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
   return B200_OK;
 }
 extern "C" int b200_memcpy_d2h(b200_ctx *ctx, void *dst, const void *src, size_t bytes) {
+  B200_ENTER(ctx);
   ARG_CHECK(ctx, "ctx is NULL");
   if (bytes) CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   return B200_OK;
 }
 extern "C" int b200_memcpy_d2d(b200_ctx *ctx, void *dst, const void *src, size_t bytes) {
+  B200_ENTER(ctx);
   ARG_CHECK(ctx, "ctx is NULL");
   if (bytes) CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
   return B200_OK;
 }
 extern "C" int b200_memset_zero(b200_ctx *ctx, void *dst, size_t bytes) {
+  B200_ENTER(ctx);
   ARG_CHECK(ctx, "ctx is NULL");
   if (bytes) CUDA_TRY(cudaMemsetAsync(dst, 0, bytes, ctx->stream));
   return B200_OK;
@@ -301,6 +329,7 @@ extern "C" int b200_event_destroy(void *ev) {
   return B200_OK;
 }
 extern "C" int b200_event_record(b200_ctx *ctx, void *ev) {
+  B200_ENTER(ctx);
   ARG_CHECK(ctx && ev, "NULL");
   CUDA_TRY(cudaEventRecord((cudaEvent_t)ev, ctx->stream));
   return B200_OK;
@@ -312,11 +341,13 @@ extern "C" int b200_event_elapsed_ms(void *start, void *stop, float *ms) {
   return B200_OK;
 }
 extern "C" int b200_launch_count(b200_ctx *ctx, uint64_t *count) {
+  B200_ENTER(ctx);
   ARG_CHECK(ctx && count, "NULL");
   *count = ctx->launches;
   return B200_OK;
 }
 extern "C" int b200_add_launches(b200_ctx *ctx, uint64_t n) {
+  B200_ENTER(ctx);
   ARG_CHECK(ctx, "NULL");
   ctx->launches += n;
   return B200_OK;

@@ -140,6 +140,7 @@ __global__ void __launch_bounds__(TPB) max_norm_kernel(float *__restrict__ w, in
 extern "C" int b200_sgd_multi_tensor(b200_ctx *ctx, int ntensors, const b200_sgd_tensor *tensors_dev,
                                      const b200_sgd_tensor *tensors_host, double decay,
                                      const int64_t *count_dev, int write_back_grad) {
+  B200_ENTER(ctx);
   return b200_sgd_multi_tensor_ex(ctx, ntensors, tensors_dev, tensors_host, decay, const_cast<int64_t *>(count_dev),
                                   write_back_grad ? B200_SGD_WRITE_BACK_GRAD : 0);
 }
@@ -147,17 +148,15 @@ extern "C" int b200_sgd_multi_tensor(b200_ctx *ctx, int ntensors, const b200_sgd
 extern "C" int b200_sgd_multi_tensor_ex(b200_ctx *ctx, int ntensors, const b200_sgd_tensor *tensors_dev,
                                         const b200_sgd_tensor *tensors_host, double decay, int64_t *count_dev,
                                         int flags) {
+  B200_ENTER(ctx);
   ARG_CHECK(ctx && tensors_dev && tensors_host && count_dev, "NULL pointer");
   if (ntensors <= 0) return B200_OK;
   size_t max_n = 0;
   for (int i = 0; i < ntensors; ++i) max_n = tensors_host[i].n > max_n ? (size_t)tensors_host[i].n : max_n;
   if (ntensors == 1 && max_n >= (1u << 20)) {
     // one big tensor: one 1024-thread CTA per SM, grid-stride inside (1024 x 12 x 16 B in flight per SM)
-    static bool attr = false;
-    if (!attr) {
+    if (ONCE_PER_DEVICE(ctx))
       CUDA_TRY(cudaFuncSetAttribute(sgd_kernel<TPB_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, SGD_BIG_SMEM));
-      attr = true;
-    }
     const int sms = ctx->sm_budget > 0 ? ctx->sm_budget : ctx->sm_count;
     size_t blocks = (max_n / 4 + (size_t)TPB_BIG * UNROLL - 1) / ((size_t)TPB_BIG * UNROLL);
     if (blocks > (size_t)sms) blocks = (size_t)sms;

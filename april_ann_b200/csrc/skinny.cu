@@ -609,8 +609,7 @@ int skinny_fwd(b200_ctx *ctx, int M, int N, int K, const float *X, int ldx, cons
       const int grid = (M + 31) / 32;
       NT_DISPATCH(N, {
         auto kern = skinny_fwd_rows_kernel<NT>;
-        static bool attr = false;
-        if (!attr) { CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
+        if (ONCE_PER_DEVICE(ctx)) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         kern<<<grid, 512, smem, ctx->stream>>>(M, N, K, X, ldx, W, ldw, bias, act, Y, ldy);
       });
       LAUNCH_CHECK(ctx);
@@ -630,6 +629,7 @@ int skinny_fwd(b200_ctx *ctx, int M, int N, int K, const float *X, int ldx, cons
 extern "C" int b200_output_layer_fused(b200_ctx *ctx, int M, int N, int K, const float *X, int ldx, const float *W, int ldw,
                                        const float *bias, const float *target, float *logits, float *logp,
                                        float *loss_rows, float *grad, int dact, float *dX, int lddx) {
+  B200_ENTER(ctx);
   ARG_CHECK(ctx && X && W && target, "NULL pointer");
   ARG_CHECK(M >= 1 && N >= 3 && K >= 1, "bad sizes");
   const bool ok = N <= SK_MAXN && (K % 4 == 0) && (ldx % 4 == 0) && (ldw % 4 == 0) && al16(X) && al16(W) &&

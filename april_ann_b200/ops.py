@@ -261,3 +261,177 @@ def maxpool_bwd(dy, argmax, x_shape, kernel, step=None, ctx=None):
     dx = DeviceArray(ctx, x_shape)
     check(lib.b200_maxpool_bwd(ctx.h, *[C.c_int(v) for v in (B, Cc, H, W, kh, kw, sh, sw)], ddy.ptr, darg.ptr, dx.ptr))
     return dx.numpy()
+
+
+# ---- BLAS level 1/2 seam (mathcore/c_src/cblas_headers.h:240-535) ----------------------------------
+def sgemv(transA, alpha, A, x, beta=0.0, y0=None, incx=1, incy=1, ctx=None):
+    """y = alpha*op(A)*x + beta*y, A [M,N] row-major (matrix:gemv, gemv.cu:44).  x / y are passed with
+    their BLAS increments: element i of the vector lives at index i*inc of the buffer."""
+    ctx = ctx or get_context()
+    A = np.ascontiguousarray(A, _f32)
+    M, N = A.shape
+    rows = N if transA else M
+    xb = np.ascontiguousarray(x, _f32).reshape(-1)
+    yb = np.zeros(rows * incy, _f32) if y0 is None else np.ascontiguousarray(y0, _f32).reshape(-1).copy()
+    dA, dx, dy = _dev(ctx, A), _dev(ctx, xb), _dev(ctx, yb)
+    check(lib.b200_sgemv(ctx.h, C.c_int(int(transA)), C.c_int(M), C.c_int(N), C.c_float(alpha), dA.ptr, C.c_int(N),
+                         dx.ptr, C.c_int(incx), C.c_float(beta), dy.ptr, C.c_int(incy)))
+    return dy.numpy()
+
+
+def sger(alpha, x, y, A0, incx=1, incy=1, ctx=None):
+    """A += alpha * x y^T (matrix:ger, ger.cu:42)."""
+    ctx = ctx or get_context()
+    A0 = np.ascontiguousarray(A0, _f32)
+    M, N = A0.shape
+    dx, dy = _dev(ctx, np.ascontiguousarray(x, _f32).reshape(-1)), _dev(ctx, np.ascontiguousarray(y, _f32).reshape(-1))
+    dA = _dev(ctx, A0)
+    check(lib.b200_sger(ctx.h, C.c_int(M), C.c_int(N), C.c_float(alpha), dx.ptr, C.c_int(incx), dy.ptr, C.c_int(incy),
+                        dA.ptr, C.c_int(N)))
+    return dA.numpy()
+
+
+def saxpy(alpha, x, y, ctx=None):
+    ctx = ctx or get_context()
+    x, y = np.ascontiguousarray(x, _f32), np.ascontiguousarray(y, _f32)
+    dx, dy = _dev(ctx, x), _dev(ctx, y)
+    check(lib.b200_saxpy(ctx.h, C.c_size_t(x.size), C.c_float(alpha), dx.ptr, dy.ptr))
+    return dy.numpy()
+
+
+def sscal(alpha, x, ctx=None):
+    ctx = ctx or get_context()
+    x = np.ascontiguousarray(x, _f32)
+    dx = _dev(ctx, x)
+    check(lib.b200_sscal(ctx.h, C.c_size_t(x.size), C.c_float(alpha), dx.ptr))
+    return dx.numpy()
+
+
+def scopy(x, ctx=None):
+    ctx = ctx or get_context()
+    x = np.ascontiguousarray(x, _f32)
+    dx, dy = _dev(ctx, x), DeviceArray(ctx, x.shape)
+    check(lib.b200_scopy(ctx.h, C.c_size_t(x.size), dx.ptr, dy.ptr))
+    return dy.numpy()
+
+
+def cmul(x, y, ctx=None):
+    """y *= x (matCmul)."""
+    ctx = ctx or get_context()
+    x, y = np.ascontiguousarray(x, _f32), np.ascontiguousarray(y, _f32)
+    dx, dy = _dev(ctx, x), _dev(ctx, y)
+    check(lib.b200_cmul(ctx.h, C.c_size_t(x.size), dx.ptr, dy.ptr))
+    return dy.numpy()
+
+
+def ssum(x, ctx=None):
+    ctx = ctx or get_context()
+    x = np.ascontiguousarray(x, _f32)
+    dx, out = _dev(ctx, x), DeviceArray(ctx, (1,))
+    check(lib.b200_sum(ctx.h, C.c_size_t(x.size), dx.ptr, out.ptr))
+    return float(out.numpy()[0])
+
+
+def nrm2sq(xs, ctx=None):
+    """sum over the given arrays of sum(x^2), accumulated in one device scalar (the global gradient
+    norm of supervised.lua:805-811 is its square root)."""
+    ctx = ctx or get_context()
+    out = DeviceArray(ctx, (1,))
+    out.zero()
+    keep = []
+    for x in xs:
+        x = np.ascontiguousarray(x, _f32)
+        dx = _dev(ctx, x)
+        keep.append(dx)
+        check(lib.b200_nrm2sq(ctx.h, C.c_size_t(x.size), dx.ptr, out.ptr))
+    return float(out.numpy()[0])
+
+
+def bias_fwd(x, b, ctx=None):
+    ctx = ctx or get_context()
+    x = np.ascontiguousarray(x, _f32)
+    dx, db, dy = _dev(ctx, x), _dev(ctx, np.ascontiguousarray(b, _f32).reshape(-1)), DeviceArray(ctx, x.shape)
+    check(lib.b200_bias_fwd(ctx.h, C.c_int(x.shape[0]), C.c_int(x.shape[1]), dx.ptr, db.ptr, dy.ptr))
+    return dy.numpy()
+
+
+def conv_bias_fwd(x, b, ctx=None):
+    ctx = ctx or get_context()
+    x = np.ascontiguousarray(x, _f32)
+    B, n, H, W = x.shape
+    dx, db, dy = _dev(ctx, x), _dev(ctx, np.ascontiguousarray(b, _f32).reshape(-1)), DeviceArray(ctx, x.shape)
+    check(lib.b200_conv_bias_fwd(ctx.h, C.c_int(B), C.c_int(n), C.c_int(H * W), dx.ptr, db.ptr, dy.ptr))
+    return dy.numpy()
+
+
+def gather_rows(data, idx, ctx=None):
+    ctx = ctx or get_context()
+    data = np.ascontiguousarray(data, _f32)
+    idx = np.ascontiguousarray(idx, np.int32)
+    dd, di = _dev(ctx, data), DeviceArray.from_numpy(ctx, idx, np.int32)
+    out = DeviceArray(ctx, (idx.size, data.shape[1]))
+    check(lib.b200_gather_rows(ctx.h, C.c_int(idx.size), C.c_int(data.shape[1]), dd.ptr, di.ptr, out.ptr))
+    return out.numpy()
+
+
+# ---- SURVEY.md 8(f) kernels ------------------------------------------------------------------------
+ACT.update({"log_logistic": 7, "softplus": 8, "softsign": 9, "leaky_relu": 10, "hardtanh": 11})
+
+
+def _act_params(kind, leak=0.01, inf=-1.0, sup=1.0):
+    return (leak, 0.0) if kind == "leaky_relu" else ((inf, sup) if kind == "hardtanh" else (0.0, 0.0))
+
+
+def actf_fwd_ex(kind, x, ctx=None, **params):
+    ctx = ctx or get_context()
+    x = np.ascontiguousarray(x, _f32)
+    p0, p1 = _act_params(kind, **params)
+    dx, dy = _dev(ctx, x), DeviceArray(ctx, x.shape)
+    check(lib.b200_actf_fwd_ex(ctx.h, C.c_int(ACT[kind]), C.c_float(p0), C.c_float(p1), C.c_size_t(x.size), dx.ptr, dy.ptr))
+    return dy.numpy()
+
+
+def actf_bwd_ex(kind, x, y, dy, ctx=None, **params):
+    ctx = ctx or get_context()
+    x, y, dy = (np.ascontiguousarray(a, _f32) for a in (x, y, dy))
+    p0, p1 = _act_params(kind, **params)
+    d_x, d_y, d_dy, d_dx = _dev(ctx, x), _dev(ctx, y), _dev(ctx, dy), DeviceArray(ctx, x.shape)
+    check(lib.b200_actf_bwd_ex(ctx.h, C.c_int(ACT[kind]), C.c_float(p0), C.c_float(p1), C.c_size_t(x.size), d_x.ptr,
+                               d_y.ptr, d_dy.ptr, d_dx.ptr))
+    return d_dx.numpy()
+
+
+def zero_one_loss(out, target, TH=0.5, ctx=None):
+    ctx = ctx or get_context()
+    out, target = np.ascontiguousarray(out, _f32), np.ascontiguousarray(target, _f32)
+    M, Cc = out.shape
+    d_o, d_t, rows = _dev(ctx, out), _dev(ctx, target), DeviceArray(ctx, (M,))
+    check(lib.b200_zero_one_loss(ctx.h, C.c_int(M), C.c_int(Cc), d_o.ptr, d_t.ptr, C.c_int(target.shape[1]), C.c_float(TH),
+                                 rows.ptr))
+    return rows.numpy()
+
+
+class DropoutStream:
+    """The device-side MT19937 of the dropout component, seeded like `random(seed)`: mask(n, prob) returns
+    the next n mask values of the reference's stream (dropout_component.cc:91-95)."""
+
+    def __init__(self, seed, ctx=None):
+        from . import random as _random
+        self.ctx = ctx or get_context()
+        lib.b200_mt_state_bytes.restype = C.c_size_t
+        nbytes = lib.b200_mt_state_bytes()
+        # same state the host generator has right after seeding: 624 words after the first reload, nothing read
+        from ._lib import lib as _l
+        r = _random(seed)
+        words = (C.c_uint32 * 624)()
+        nxt = C.c_int32()
+        check(_l.b200h_random_export_state(r.h, words, C.byref(nxt)))
+        host = np.zeros(nbytes // 4, dtype=np.uint32)
+        host[:624] = np.frombuffer(words, dtype=np.uint32)
+        host[624] = np.uint32(nxt.value)
+        self.state = DeviceArray.from_numpy(self.ctx, host, np.uint32)
+
+    def mask(self, n, prob):
+        m = DeviceArray(self.ctx, (n,))
+        check(lib.b200_dropout_mask(self.ctx.h, self.state.ptr, C.c_size_t(n), C.c_float(prob), m.ptr))
+        return m.numpy()

@@ -45,7 +45,14 @@ enum {
   B200_ACT_RELU = 3,       /* derivative (x>0), evaluated as (y>0) */
   B200_ACT_SOFTMAX = 4,
   B200_ACT_LOG_SOFTMAX = 5,
-  B200_ACT_LINEAR = 6
+  B200_ACT_LINEAR = 6,
+  /* the cheap activations of SURVEY.md 8(f)4 (activation_function_kernels.cu:52-182); element-wise launches
+   * (b200_actf_fwd_ex / _bwd_ex), not fused into the contraction epilogue */
+  B200_ACT_LOG_LOGISTIC = 7,  /* x<-10 ? x : -log1p(e^-x); derivative cancelled by cross-entropy (identity) */
+  B200_ACT_SOFTPLUS = 8,      /* x>10 ? x : log1p(e^x);    derivative from the INPUT: logistic(x) */
+  B200_ACT_SOFTSIGN = 9,      /* x/(1+|x|);                derivative from the OUTPUT, clamped: 1/(1+|y|)^2 */
+  B200_ACT_LEAKY_RELU = 10,   /* p0 = leak;                derivative from the INPUT: x>0 ? 1 : leak */
+  B200_ACT_HARDTANH = 11      /* clamp(x, p0, p1);         derivative from the INPUT: (x<p0 || x>p1) ? 0 : 1 */
 };
 
 /* math modes for the contractions */
@@ -144,6 +151,23 @@ int b200_linear_bwd_weight(b200_ctx *ctx, int M, int N, int K, const float *dY, 
 int b200_actf_fwd(b200_ctx *ctx, int act, size_t n, const float *x, float *y);
 /* dx = act'(.) * dy ; y = activation output (relu: y>0 <=> x>0) */
 int b200_actf_bwd(b200_ctx *ctx, int act, size_t n, const float *y, const float *dy, float *dx);
+/* parametrised / input-derivative activations (p0, p1: leak / inf, sup).  bwd: x = activation input, y = output;
+ * either may be NULL when the kind does not need it */
+int b200_actf_fwd_ex(b200_ctx *ctx, int act, float p0, float p1, size_t n, const float *x, float *y);
+int b200_actf_bwd_ex(b200_ctx *ctx, int act, float p0, float p1, size_t n, const float *x, const float *y,
+                     const float *dy, float *dx);
+/* PReLU (prelu_actf_component.cc:55-114): y = x>0 ? x : a[n]*x (scalar: one a); da = beta*da + scale * sum (x<0)*x*dy;
+ * tmp = M*N floats of workspace */
+int b200_prelu_fwd(b200_ctx *ctx, int M, int N, const float *x, const float *a, int scalar, float *y);
+int b200_prelu_bwd(b200_ctx *ctx, int M, int N, const float *x, const float *a, int scalar, const float *dy, float *dx);
+int b200_prelu_grad(b200_ctx *ctx, int M, int N, const float *x, const float *dy, int scalar, float scale, float beta,
+                    float *da, float *tmp);
+/* dropout (dropout_component.cc:67-134): mask[i] = (i-th rand() of the component's MT19937) < prob ? 0 : 1, drawn
+ * on the device in the reference's stream order.  mt_state_dev: b200_mt_state_bytes() bytes = 624 state words
+ * (after MTRand's reload) + int32 position of the next unread word.  b200_mask_apply: y = mask<0.5 ? value : x */
+size_t b200_mt_state_bytes(void);
+int b200_dropout_mask(b200_ctx *ctx, void *mt_state_dev, size_t n, float prob, float *mask);
+int b200_mask_apply(b200_ctx *ctx, size_t n, const float *x, const float *mask, float value, float *y);
 int b200_bias_fwd(b200_ctx *ctx, int M, int N, const float *x, const float *b, float *y);
 int b200_bias_grad(b200_ctx *ctx, int M, int N, const float *dy, int lddy, float scale,
                    float beta, float *db);
@@ -163,6 +187,10 @@ int b200_mse_loss_grad(b200_ctx *ctx, int M, int C, const float *out, const floa
                        float *loss_rows, float *grad);
 int b200_ce_loss_grad(b200_ctx *ctx, int M, int C, const float *log_out, const float *target,
                       float *loss_rows, float *grad);
+/* zero-one loss (zero_one_loss_function.cc:39-132): C == 1: (out > TH) != (target > 0.5); else arg-max of the row
+ * against the arg-max of a dense target (target_cols == C) or a 1-based class label (target_cols == 1) */
+int b200_zero_one_loss(b200_ctx *ctx, int M, int C, const float *out, const float *target, int target_cols, float TH,
+                       float *loss_rows);
 /* one pass: logits -> logp (may be NULL), loss_rows, grad = exp(clamp(logp)) - target */
 int b200_log_softmax_mcce_fused(b200_ctx *ctx, int M, int C, const float *logits,
                                 const float *target, float *logp, float *loss_rows, float *grad);
@@ -207,12 +235,32 @@ int b200_sgd_multi_tensor_ex(b200_ctx *ctx, int ntensors, const b200_sgd_tensor 
                              const b200_sgd_tensor *tensors_host, double decay, int64_t *count_dev,
                              int flags);
 int b200_counter_increment(b200_ctx *ctx, int64_t *count_dev);
+/* global gradient-norm clip of train_step (packages/trainable/lua_src/supervised.lua:805-811): one norm over
+ * the whole (flat) gradient arena, then g *= max_norm/norm when norm > max_norm.  norm2sq_dev: device float. */
+int b200_grad_clip(b200_ctx *ctx, size_t n, float *grads, float max_norm, float *norm2sq_dev);
+/* adagrad / rmsprop / adadelta (packages/ann/optimizer/lua_src/optimizer_{adagrad,rmsprop,adadelta}.lua) as
+ * one multi-tensor launch.  State per tensor: u (rmsprop Eupdate / adadelta lr*update), s1 (Egradient / Erms),
+ * s2 (adadelta Eupdate).  b200_optimizer_lookahead is rmsprop's w -= momentum*Eupdate before the gradient is
+ * evaluated (optimizer_rmsprop.lua:44-51). */
+enum { B200_OPT_SGD = 0, B200_OPT_ADAGRAD = 1, B200_OPT_RMSPROP = 2, B200_OPT_ADADELTA = 3 };
+typedef struct {
+  float *w, *g, *u, *s1, *s2;
+  uint64_t n;
+  int32_t rows, cols;
+  float lr, momentum, decay, epsilon, weight_decay, max_norm_penalty;
+  int32_t write_back_grad, pad_;
+} b200_opt_tensor;
+int b200_optimizer_multi_tensor(b200_ctx *ctx, int algo, int ntensors, const b200_opt_tensor *tensors_dev,
+                                const b200_opt_tensor *tensors_host, int64_t *count_dev, int increment_count);
+int b200_optimizer_lookahead(b200_ctx *ctx, int ntensors, const b200_opt_tensor *tensors_dev,
+                             const b200_opt_tensor *tensors_host);
 
 /* ------------------------------------------------------------------ replica group over NVLink peer memory
  * New relative to the reference (single device, gpu_helper.h:65-68).  b200_dp_fused_update is the
- * data-parallel update as one kernel: gradient reduce-scatter (every rank pushes its gradients of the
- * peers' shards into their receive blocks with P2P stores), the SGD step above on the rank's shard,
- * all-gather of the updated weights (P2P stores into every replica).  The arenas of every rank are mapped into each process with CUDA IPC
+ * data-parallel update as one kernel: gradient reduce-scatter (by default every rank PULLS the peers'
+ * gradients of its own shard with P2P loads; B200_DP_PUSH=1 selects the push variant, P2P stores into the
+ * owners' receive blocks), the SGD step above on the rank's shard, all-gather of the updated weights
+ * (P2P stores into every replica).  The arenas of every rank are mapped into each process with CUDA IPC
  * (b200_ipc_export / _import: the 64-byte handle travels over the host-side rendezvous).  Ordering
  * between GPUs: per (bucket, rank) step tags in `flags` (b200_dp_flags_bytes() bytes per rank, zeroed
  * once); b200_dp_wait, at the end of a step, returns once every rank's shard of every bucket has landed. */

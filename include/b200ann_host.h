@@ -24,7 +24,8 @@ typedef struct b200_component b200_component;
 typedef struct b200_trainer b200_trainer;
 typedef struct b200_random b200_random;
 
-enum { B200_LOSS_MSE = 0, B200_LOSS_CROSS_ENTROPY = 1, B200_LOSS_MULTI_CLASS_CROSS_ENTROPY = 2 };
+enum { B200_LOSS_MSE = 0, B200_LOSS_CROSS_ENTROPY = 1, B200_LOSS_MULTI_CLASS_CROSS_ENTROPY = 2,
+       B200_LOSS_ZERO_ONE = 3 /* ann.loss.zero_one: validation / use only, not differentiable */ };
 enum { B200_TOKEN_INPUT = 0, B200_TOKEN_OUTPUT = 1, B200_TOKEN_ERROR_INPUT = 2, B200_TOKEN_ERROR_OUTPUT = 3 };
 
 int b200_add_launches(b200_ctx *ctx, uint64_t n);   /* graph replays: kernels launched per replay */
@@ -35,6 +36,9 @@ void b200h_random_free(b200_random *r);
 double b200h_random_rand(b200_random *r, double n);
 uint32_t b200h_random_randint(b200_random *r, uint32_t n);     /* [0, n] */
 int b200h_random_shuffle(b200_random *r, int size, int *out);   /* 0-based permutation */
+/* the generator's 624 state words + the index of the next unread one (624: block exhausted): the layout
+ * b200_dropout_mask continues from (b200_mt_state_bytes) */
+int b200h_random_export_state(b200_random *r, uint32_t *words624, int32_t *next);
 
 /* component constructors (ownership: the caller frees its handle; stacks share ownership) */
 b200_component *b200h_stack_new(const char *name);
@@ -43,7 +47,15 @@ b200_component *b200h_hyperplane_new(const char *name, unsigned in, unsigned out
                                      const char *bias_name, const char *dot_weights, const char *bias_weights);
 b200_component *b200h_dot_product_new(const char *name, const char *weights, unsigned in, unsigned out);
 b200_component *b200h_bias_new(const char *name, const char *weights, unsigned size);
+/* kind: logistic tanh relu softmax log_softmax linear log_logistic softplus softsign leaky_relu hardtanh */
 b200_component *b200h_actf_new(const char *kind, const char *name);
+/* leaky_relu: p0 = leak; hardtanh: p0 = inf, p1 = sup (leaky_relu_actf_component.cc, hardtanh_actf_component.cc) */
+b200_component *b200h_actf_new_ex(const char *kind, const char *name, float p0, float p1);
+/* ann.components.actf.prelu{ size=, scalar=, name=, weights= }  (prelu_actf_component.cc) */
+b200_component *b200h_prelu_new(const char *name, const char *weights, unsigned size, int scalar);
+/* ann.components.dropout{ name=, size=, prob=, value=, random=, norm= }  (bind_ann_base.lua.cc:1643-1670);
+ * the component copies the generator: its mask stream continues from the state `random` has now */
+b200_component *b200h_dropout_new(const char *name, b200_random *random, float prob, float value, int norm, unsigned size);
 b200_component *b200h_rewrap_new(const char *name, const int *size, int ndims);
 b200_component *b200h_flatten_new(const char *name);
 b200_component *b200h_convolution_new(const char *name, const char *weights, const int *kernel, const int *step,
@@ -67,7 +79,8 @@ int b200h_trainer_set_flag(b200_trainer *t, const char *flag, int value);
 int b200h_trainer_num_weights(b200_trainer *t, int *n);
 int b200h_trainer_weight_name(b200_trainer *t, int i, char *buf, int buflen);
 int b200h_trainer_weight_dims(b200_trainer *t, const char *name, int *dims2);
-/* which: 0 weights, 1 gradients (of the last step), 2 momentum/update buffer */
+/* which: 0 weights, 1 gradients (of the last step), 2 momentum/update buffer (sgd update, rmsprop Eupdates,
+ * adadelta update), 3 first optimizer state (adagrad/adadelta Egradients, rmsprop Erms), 4 second (adadelta Eupdates) */
 int b200h_trainer_tensor_get(b200_trainer *t, const char *name, int which, float *host);
 int b200h_trainer_tensor_set(b200_trainer *t, const char *name, int which, const float *host);
 int b200h_trainer_num_parameters(b200_trainer *t, uint64_t *n);
@@ -77,8 +90,23 @@ int b200h_trainer_output_size(b200_trainer *t, int *n);
 /* train_step / validate_step (supervised.lua:725-862): host bunch in, bunch-mean loss out */
 int b200h_trainer_train_step(b200_trainer *t, const float *x, const float *target, int bunch, float *loss,
                              float *loss_rows /* may be NULL */);
+/* train_step(input, target, loss, optimizer, bunch_size, smooth, mask, max_gradients_norm) of
+ * supervised.lua:725-821: smoothing_bunch = the bunch_size argument (0: the trainer's bunch_size, as the reference
+ * does -- NOT the row count), max_gradients_norm = global gradient-norm clip (0: off) */
+int b200h_trainer_train_step_ex(b200_trainer *t, const float *x, const float *target, int bunch, int smoothing_bunch,
+                                double max_gradients_norm, float *loss, float *loss_rows);
 int b200h_trainer_validate_step(b200_trainer *t, const float *x, const float *target, int bunch, float *loss,
                                 float *loss_rows);
+/* use_dataset (supervised.lua:1291-1430): forward only over n patterns; y holds n*output_size floats */
+int b200h_trainer_use_dataset(b200_trainer *t, const float *x, int n, float *y);
+/* ann.optimizer.{sgd,adagrad,rmsprop,adadelta}: selects the optimizer (options reset to its defaults, state
+ * cleared); its state is readable / writable with b200h_trainer_tensor_get/set (which 2, 3, 4) */
+int b200h_trainer_set_optimizer(b200_trainer *t, const char *name);
+/* number of optimizer:execute calls so far -- with the weights and the state tensors this is everything
+ * a checkpoint needs (optimizer_sgd.lua:102-119 exports options + count + update) */
+int b200h_trainer_get_count(b200_trainer *t, int64_t *count);
+int b200h_trainer_set_count(b200_trainer *t, int64_t count);
+int b200h_trainer_set_loss_threshold(b200_trainer *t, float th);   /* zero_one: TH of the two-class case */
 /* train_dataset / validate_dataset (supervised.lua:1149-1226,1291-1360): order = shuffled pattern
  * indices (0-based) or NULL for sequential; returns loss:get_accum_loss() */
 int b200h_trainer_train_dataset(b200_trainer *t, const float *x, const float *target, int n, const int *order,

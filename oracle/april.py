@@ -52,6 +52,53 @@ def relu_der(x):
     return np.where(x > 0, f32(1), f32(0)).astype(f32)  # :1115-1124
 
 
+def log_logistic(x):
+    # cmath_overloads.h:993-1003: x < -10 ? x : -log1p(exp(-x))
+    x = np.asarray(x, dtype=f32)
+    with np.errstate(over="ignore"):
+        return np.where(x < f32(-10.0), x, -np.log1p(np.exp(-x, dtype=f32), dtype=f32)).astype(f32)
+
+
+def softplus(x):
+    # cmath_overloads.h:1017-1023: x > 10 ? x : log1p(exp(x))
+    x = np.asarray(x, dtype=f32)
+    with np.errstate(over="ignore"):
+        return np.where(x > f32(10.0), x, np.log1p(np.exp(x, dtype=f32), dtype=f32)).astype(f32)
+
+
+def softplus_der(x):
+    return logistic(x)  # m_softplus_der: from the INPUT  (:1084-1090)
+
+
+def softsign(x):
+    x = np.asarray(x, dtype=f32)
+    return (x / (f32(1.0) + np.abs(x))).astype(f32)  # :1008-1014
+
+
+def softsign_der(y):
+    # :1073-1081, evaluated on the (clamped) OUTPUT
+    v = np.clip(y, f32(-1.0) + NEAR_ZERO, f32(1.0) - NEAR_ZERO).astype(f32)
+    aux = (f32(1.0) + np.abs(v)).astype(f32)
+    return (f32(1.0) / (aux * aux)).astype(f32)
+
+
+def leaky_relu(x, leak):
+    return np.where(x > 0, x, f32(leak) * x).astype(f32)  # :736-744
+
+
+def leaky_relu_der(x, leak):
+    return np.where(x > 0, f32(1), f32(leak)).astype(f32)  # :1101-1109
+
+
+def hardtanh(x, inf, sup):
+    return np.clip(x, f32(inf), f32(sup)).astype(f32)  # matClamp, hardtanh_actf_component.cc:37-40
+
+
+def hardtanh_der(x, inf, sup):
+    # m_clamp_der :1143-1153, from the INPUT
+    return np.where((x < f32(inf)) | (x > f32(sup)), f32(0), f32(1)).astype(f32)
+
+
 def softmax_rows(x):
     """activation_function_kernels.cu:209-248 (CPU branch): subtract the
     (clamped) row MINIMUM, exp and sum in double, scale by float(1/sum)."""
@@ -158,13 +205,24 @@ class Bias(Component):
 class Actf(Component):
     """activation_function_component.cc:48-120 + the concrete *_actf_component.cc."""
 
-    def __init__(self, kind):
+    def __init__(self, kind, **params):
         self.kind = kind
+        self.params = params  # leaky_relu: leak ; hardtanh: inf, sup
 
     def forward(self, x, during_training=False):
         self.x = x
         k = self.kind
-        if k == "logistic":
+        if k == "log_logistic":
+            y = log_logistic(x)  # log_logistic_actf_component.cc:39-42
+        elif k == "softplus":
+            y = softplus(x)
+        elif k == "softsign":
+            y = softsign(x)
+        elif k == "leaky_relu":
+            y = leaky_relu(x, self.params.get("leak", 0.01))
+        elif k == "hardtanh":
+            y = hardtanh(x, self.params.get("inf", -1.0), self.params.get("sup", 1.0))
+        elif k == "logistic":
             y = logistic(x)
         elif k == "tanh":
             y = antisym_logistic(x)
@@ -192,9 +250,79 @@ class Actf(Component):
             return dy
         if k == "softmax":
             return softmax_der_rows(self.y, dy)
-        if k == "log_softmax":
-            return dy.copy()  # log_softmax_actf_component.cc:44-52 (identity)
+        if k in ("log_softmax", "log_logistic"):
+            # log_softmax_actf_component.cc:44-52, log_logistic_actf_component.cc:44-53: the derivative is
+            # cancelled by the (multi-class) cross-entropy derivative -> identity
+            return dy.copy()
+        if k == "softplus":
+            return (softplus_der(self.x) * dy).astype(f32)  # softplus_actf_component.cc:44-51
+        if k == "softsign":
+            return (softsign_der(self.y) * dy).astype(f32)
+        if k == "leaky_relu":
+            return (leaky_relu_der(self.x, self.params.get("leak", 0.01)) * dy).astype(f32)
+        if k == "hardtanh":
+            return (hardtanh_der(self.x, self.params.get("inf", -1.0), self.params.get("sup", 1.0)) * dy).astype(f32)
         raise ValueError(k)
+
+
+class PReLU(Component):
+    """prelu_actf_component.cc:55-114: y = x>0 ? x : a*x with a learnable a[size,1] (or one scalar);
+    gradient da = sum over the bunch of (x<0)*x*dy; shared count += 1."""
+
+    def __init__(self, size, weights_name, scalar=False):
+        self.size, self.weights_name, self.scalar = size, weights_name, scalar
+
+    def build(self, input_size, weights):
+        self.size = self.size or input_size
+        if self.weights_name not in weights:
+            weights[self.weights_name] = np.zeros((1 if self.scalar else self.size, 1), dtype=f32)
+        self.w = weights
+        return self.size
+
+    def _a(self):
+        a = self.w[self.weights_name][:, 0]
+        return a[0] if self.scalar else a[None, :]
+
+    def forward(self, x, during_training=False):
+        self.x = x
+        return np.where(x > 0, x, (self._a() * x).astype(f32)).astype(f32)
+
+    def backprop(self, dy):
+        self.dy = dy
+        a = self._a()
+        return (np.where(self.x > 0, f32(1), a + f32(0) * self.x).astype(f32) * dy).astype(f32)
+
+    def compute_gradients(self, grads, counts):
+        n = self.weights_name
+        e = (np.where(self.x < 0, f32(1), f32(0)) * self.x).astype(f32) * self.dy
+        g = e.sum(dtype=f32).reshape(1, 1) if self.scalar else e.sum(axis=0, dtype=f32).reshape(-1, 1)
+        grads[n] = (grads.get(n, 0) + g).astype(f32)
+        counts[n] = counts.get(n, 0) + 1
+
+
+class Dropout(Component):
+    """dropout_component.cc:67-134: during training every unit is replaced by `value` with probability
+    `prob`, the mask drawn element by element (row-major) from the component's MTRand as
+    `rand() < prob`; backprop zeroes the same units; outside training the output is scaled by 1-prob
+    (norm=true, the binding's default, bind_ann_base.lua.cc:1652-1668)."""
+
+    def __init__(self, random, prob=0.5, value=0.0, norm=True):
+        self.random, self.prob, self.value, self.norm = random, prob, value, norm
+        self.mask = None
+
+    def forward(self, x, during_training=False):
+        if self.prob > 0.0 and (during_training or self.norm):
+            if during_training:
+                r = self.random.rand_array(x.size, 1.0)
+                self.mask = np.where(r < float(f32(self.prob)), f32(0), f32(1)).astype(f32).reshape(x.shape)
+                return np.where(self.mask < f32(0.5), f32(self.value), x).astype(f32)
+            return (x * f32(1.0 - f32(self.prob))).astype(f32)
+        return x
+
+    def backprop(self, dy):
+        if self.mask is not None and self.prob > 0.0:
+            return np.where(self.mask < f32(0.5), f32(0), dy).astype(f32)
+        return dy
 
 
 class Rewrap(Component):
@@ -506,6 +634,30 @@ class CrossEntropy(Loss):
         return (np.exp(np.clip(o, le, l1e).astype(f32), dtype=f32) - t).astype(f32)
 
 
+class ZeroOne(Loss):
+    """zero_one_loss_function.cc:39-132: 0/1 error per pattern; two-class (one output, threshold TH) or
+    multi-class (arg-max of output vs arg-max of a dense target, or vs a [bunch,1] vector of 1-based
+    class labels).  First maximum wins (matMax uses a strict '>').  Not differentiable."""
+
+    def __init__(self, TH=0.5):
+        super().__init__()
+        self.TH = TH
+
+    def loss_rows(self, o, t):
+        if o.shape[1] == 1:
+            pred = o[:, 0] > f32(self.TH)
+            want = t[:, 0] > f32(0.5)
+            return (pred != want).astype(f32)
+        am = o.argmax(axis=1)
+        if t.shape[1] == o.shape[1]:
+            return (am != t.argmax(axis=1)).astype(f32)
+        assert t.shape[1] == 1, "Incorrect target matrix bunch_size"
+        return (am != (t[:, 0] - f32(1)).astype(np.int64)).astype(f32)
+
+    def gradient(self, o, t):
+        raise RuntimeError("NON DIFERENTIABLE LOSS FUNCTION")
+
+
 # ---------------------------------------------------------------------------
 # SGD  (packages/ann/optimizer/lua_src/optimizer_sgd.lua:50-100)
 # ---------------------------------------------------------------------------
@@ -518,6 +670,9 @@ class SGD:
         self.layerwise = {}
         self.count = 0
         self.update = {}
+
+    def before_eval(self, weights):
+        pass
 
     def set_option(self, name, value):
         assert name in self.DEFAULTS
@@ -584,6 +739,141 @@ def _prune_subnormal(w):
     tiny = np.finfo(f32).tiny
     w[np.abs(w) < tiny] = 0
     assert np.isfinite(w).all(), "No finite number at weights matrix!!!"
+
+
+class _Optimizer(SGD):
+    """Shared option handling (base_optimizer.lua:88-114)."""
+    DEFAULTS = {}
+
+    def before_eval(self, weights):
+        pass
+
+
+class Adagrad(_Optimizer):
+    """optimizer_adagrad.lua:20-83 (the reference's "adagrad" keeps an exponentially decayed mean of
+    squared gradients, seeded with grad^2 at count 0)."""
+    DEFAULTS = dict(learning_rate=1.0, decay=0.95, epsilon=1e-06, weight_decay=0.0, max_norm_penalty=0.0)
+
+    def __init__(self):
+        super().__init__()
+        self.Egradients = {}
+
+    def execute(self, weights, grads):
+        for name, w in weights.items():
+            E = self.Egradients.get(name)
+            if E is None:
+                E = np.zeros_like(w)
+            g = grads[name]
+            lr, decay, eps = (self.get_option_of(name, k) for k in ("learning_rate", "decay", "epsilon"))
+            l2, mnp = self.get_option_of(name, "weight_decay"), self.get_option_of(name, "max_norm_penalty")
+            if l2 > 0.0:
+                g += f32(l2) * w
+            if self.count == 0:
+                E[...] = g * g
+            else:
+                E[...] = f32(decay) * E + f32(1 - decay) * (g * g)
+            upd = (g * (f32(1.0) / (f32(eps) + np.sqrt(E)))).astype(f32)
+            w += f32(-lr) * upd
+            if mnp > 0.0:
+                _max_norm_penalty(w, mnp)
+            if self.count % 100 == 0:
+                _prune_subnormal(w)
+            self.Egradients[name] = E
+        self.count += 1
+
+
+class RMSProp(_Optimizer):
+    """optimizer_rmsprop.lua:20-100: Nesterov look-ahead w -= mt*Eupdate BEFORE the gradient is
+    evaluated; Erms = decay*Erms + (1-decay)*g^2 ; step = lr/sqrt(Erms+eps) * g (matrix:div(lr) is lr/m,
+    cmath_overloads.h:1513-1519)."""
+    DEFAULTS = dict(learning_rate=0.01, momentum=0.0, decay=0.99, epsilon=1e-06, weight_decay=0.0,
+                    max_norm_penalty=0.0)
+
+    def __init__(self):
+        super().__init__()
+        self.Eupdates, self.Erms = {}, {}
+
+    def before_eval(self, weights):
+        for name, w in weights.items():
+            mt = self.get_option_of(name, "momentum")
+            if mt > 0.0:
+                Eu = self.Eupdates.setdefault(name, np.zeros_like(w))
+                w += f32(-mt) * Eu
+
+    def execute(self, weights, grads):
+        for name, w in weights.items():
+            Eu = self.Eupdates.get(name)
+            if Eu is None:
+                Eu = np.zeros_like(w)
+            Er = self.Erms.get(name)
+            if Er is None:
+                Er = np.zeros_like(w)
+            g = grads[name]
+            lr, mt, decay, eps = (self.get_option_of(name, k) for k in ("learning_rate", "momentum", "decay", "epsilon"))
+            l2, mnp = self.get_option_of(name, "weight_decay"), self.get_option_of(name, "max_norm_penalty")
+            if l2 > 0.0:
+                g += f32(l2) * w
+            Er *= f32(decay)
+            Er += f32(1 - decay) * (g * g)
+            tmp = ((f32(lr) / np.sqrt(Er + f32(eps))) * g).astype(f32)
+            if mt > 0.0:
+                Eu *= f32(mt)
+                Eu += tmp
+            else:
+                Eu[...] = tmp
+            w -= Eu
+            if mnp > 0.0:
+                _max_norm_penalty(w, mnp)
+            if self.count % 100 == 0:
+                _prune_subnormal(w)
+            self.Erms[name] = Er
+            if mt > 0.0:
+                self.Eupdates[name] = Eu
+        self.count += 1
+
+
+class Adadelta(_Optimizer):
+    """optimizer_adadelta.lua:20-96."""
+    DEFAULTS = dict(learning_rate=1.0, momentum=0.0, decay=0.95, epsilon=1e-06, weight_decay=0.0,
+                    max_norm_penalty=0.0)
+
+    def __init__(self):
+        super().__init__()
+        self.Eupdates, self.Egradients, self.update = {}, {}, {}
+
+    def execute(self, weights, grads):
+        for name, w in weights.items():
+            mt = self.get_option_of(name, "momentum")
+            if mt > 0.0:
+                u = self.update.setdefault(name, np.zeros_like(w))
+                w += f32(mt) * u
+        for name, w in weights.items():
+            Eu = self.Eupdates.get(name)
+            if Eu is None:
+                Eu = np.zeros_like(w)
+            Eg = self.Egradients.get(name)
+            if Eg is None:
+                Eg = np.zeros_like(w)
+            u = self.update.get(name)
+            if u is None:
+                u = np.zeros_like(w)
+            g = grads[name]
+            lr, decay, eps = (self.get_option_of(name, k) for k in ("learning_rate", "decay", "epsilon"))
+            l2, mnp = self.get_option_of(name, "weight_decay"), self.get_option_of(name, "max_norm_penalty")
+            if l2 > 0.0:
+                g += f32(l2) * w
+            Eg[...] = f32(decay) * Eg + f32(1 - decay) * (g * g)
+            u[...] = -(g * (np.sqrt(Eu + f32(eps)) / np.sqrt(Eg + f32(eps)))).astype(f32)
+            Eu[...] = f32(decay) * Eu + f32(1 - decay) * (u * u)
+            w += f32(lr) * u
+            if mnp > 0.0:
+                _max_norm_penalty(w, mnp)
+            if self.count % 100 == 0:
+                _prune_subnormal(w)
+            self.Eupdates[name], self.Egradients[name] = Eu, Eg
+            u *= f32(lr)
+            self.update[name] = u
+        self.count += 1
 
 
 # ---------------------------------------------------------------------------
@@ -654,8 +944,10 @@ class SupervisedTrainer:
             w[...] = vals.reshape(w.shape)
 
     # supervised.lua:725-821
-    def train_step(self, x, t, bunch_size=None):
-        bunch_size = bunch_size or x.shape[0]
+    def train_step(self, x, t, bunch_size=None, max_gradients_norm=None):
+        # supervised.lua:757: `bunch_size or self.bunch_size or 1` -- NOT the row count of x
+        bunch_size = bunch_size or self.bunch_size or 1
+        self.optimizer.before_eval(self.weights)
         out = self.net.forward(x, True)
         tr_loss, loss_vec = self.loss.compute_loss(out, t)
         self.net.backprop(self.loss.gradient(out, t))
@@ -665,6 +957,14 @@ class SupervisedTrainer:
             for name, g in grads.items():
                 n = counts.get(name, 0) or 1
                 g *= f32(1.0 / math.sqrt(n * bunch_size))  # :797-803
+        if max_gradients_norm:
+            # supervised.lua:805-811: matrix.dict.norm2 = sqrt(sum over tensors of norm2^2)
+            nrm = math.sqrt(sum(float(np.dot(g.ravel().astype(np.float64), g.ravel().astype(np.float64)))
+                                for g in grads.values()))
+            if nrm > max_gradients_norm:
+                ratio = f32(max_gradients_norm / nrm)
+                for g in grads.values():
+                    g *= ratio
         self.grads = grads
         self.optimizer.execute(self.weights, grads)
         self.loss.accum_loss(loss_vec)
@@ -695,6 +995,15 @@ class SupervisedTrainer:
         for k in range(0, n, bs):
             self.validate_step(input_dataset[k:k + bs], output_dataset[k:k + bs])
         return self.loss.get_accum_loss()
+
+    # supervised.lua:1236-1245 / 1291-1430: forward only, bunch by bunch
+    def calculate(self, x):
+        return self.net.forward(x, False)
+
+    def use_dataset(self, input_dataset, bunch_size=None):
+        bs = bunch_size or self.bunch_size
+        outs = [self.net.forward(input_dataset[k:k + bs], False) for k in range(0, input_dataset.shape[0], bs)]
+        return np.concatenate(outs, axis=0)
 
     # supervised.lua:1556-1576: max over matching matrices of the max row 2-norm
     def norm2(self, pattern):

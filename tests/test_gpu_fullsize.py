@@ -1,0 +1,417 @@
+"""GPU parity at the sizes the bench numbers are quoted on (BASELINE.json configs C2..C5), and the
+C-ABI exports that no other test reaches.  Every comparison is against the CPU oracle (or float64
+numpy for a single contraction) on the same seeded inputs.  Tolerances:
+  * fp32 (FFMA) mode: rel-L2 <= 1e-5 per tensor (gradients/updates after a chain of layers: 2e-5)
+  * TF32 (tcgen05) mode: rel-L2 <= 2e-3 per tensor
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import MTRand  # noqa: E402
+from oracle import april as A  # noqa: E402
+
+F32_TOL = 1e-5
+TF32_TOL = 2e-3
+
+
+@pytest.fixture(scope="module")
+def ann():
+    import april_ann_b200 as ann
+    ann.get_context().set_math_mode(ann.MATH_FP32)
+    return ann
+
+
+@pytest.fixture(scope="module")
+def ops(ann):
+    from april_ann_b200 import ops
+    return ops
+
+
+def rel_l2(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def rnd(seed, *shape, lo=-1.0, hi=1.0):
+    return np.random.RandomState(seed).uniform(lo, hi, size=shape).astype(np.float32)
+
+
+def onehot(seed, M, C):
+    t = np.zeros((M, C), dtype=np.float32)
+    t[np.arange(M), np.random.RandomState(seed).randint(0, C, size=M)] = 1.0
+    return t
+
+
+class math_mode:
+    def __init__(self, ann, mode):
+        self.ann, self.mode = ann, mode
+
+    def __enter__(self):
+        self.ann.get_context().set_math_mode(self.ann.MATH_TF32 if self.mode == "tf32" else self.ann.MATH_FP32)
+
+    def __exit__(self, *a):
+        self.ann.get_context().set_math_mode(self.ann.MATH_FP32)
+
+
+def make_pair(ann, topo, bunch, loss="mcce", seed=1234, **opts):
+    ref_loss = {"mcce": A.MultiClassCrossEntropy, "mse": A.MSE}[loss]()
+    gpu_loss = {"mcce": ann.loss.multi_class_cross_entropy, "mse": ann.loss.mse}[loss]()
+    ref = A.SupervisedTrainer(A.mlp_all_all(topo), ref_loss, bunch).build()
+    tr = ann.trainable.supervised_trainer(ann.mlp.all_all.generate(topo), gpu_loss, bunch).build()
+    for k, v in opts.items():
+        ref.set_option(k, v)
+        tr.set_option(k, v)
+    ref.set_layerwise_option("b.", "weight_decay", 0)
+    tr.set_layerwise_option("b.", "weight_decay", 0)
+    ref.randomize_weights(random=MTRand(seed), inf=-1, sup=1, use_fanin=True, use_fanout=True)
+    tr.randomize_weights(random=ann.random(seed), inf=-1, sup=1, use_fanin=True, use_fanout=True)
+    return ref, tr
+
+
+# ------------------------------------------------------------------ C2 at full size, step for step
+def _f64_gradients_with_gates(w, x, t, gate1, gate2, bunch):
+    """float64 restatement of the backward pass of the 3-layer ReLU net (dot_product_component.cc:123-216,
+    bias_component.cc:87-122, multiclass_cross_entropy_loss_function.cc:61-71, supervised.lua:797-803) with the
+    ReLU gates GIVEN (relu_actf_component.cc:45-52 takes them from the sign of the pre-activation)."""
+    W = {k: v.astype(np.float64) for k, v in w.items()}
+    h1 = (x.astype(np.float64) @ W["w1"].T + W["b1"][:, 0]) * gate1
+    h2 = (h1 @ W["w2"].T + W["b2"][:, 0]) * gate2
+    z = h2 @ W["w3"].T + W["b3"][:, 0]
+    z -= z.max(axis=1, keepdims=True)
+    logp = z - np.log(np.exp(z).sum(axis=1, keepdims=True))
+    g = np.exp(np.clip(logp, np.log(1e-6), np.log(1 - 1e-6))) - t
+    d2 = (g @ W["w3"]) * gate2
+    d1 = (d2 @ W["w2"]) * gate1
+    s = 1.0 / np.sqrt(bunch)
+    return {"b1": d1.sum(0) * s, "b2": d2.sum(0) * s, "b3": g.sum(0) * s, "w1": d1.T @ x * s, "w2": d2.T @ h1 * s,
+            "w3": g.T @ h2 * s}
+
+
+@pytest.mark.parametrize("mode,tol", [("fp32", 2e-5), ("tf32", TF32_TOL)])
+def test_c2_full_size_three_steps_vs_oracle(ann, mode, tol):
+    """BASELINE configs[1] (784-2048-2048-10 ReLU / log_softmax + MCCE, bunch 1024, the bench workload)
+    at full size, three train steps on distinct bunches against the oracle.
+
+    The derivative of ReLU is discontinuous: a unit whose pre-activation lies within the rounding error of
+    zero opens its gate on one side and not on the other, and ONE flipped gate among the 2 M units moves
+    every hidden-layer gradient by ~1e-3 rel-L2 (the float32 oracle against a float64 evaluation of itself
+    shows the same: 2e-3 on step 2 of this very test).  So the comparison is done in two parts:
+      * forward side and gates: loss rows within tol; the device's gates equal the oracle's except on units
+        whose oracle pre-activation is within `amb` of zero (amb = the rounding error of the mode);
+      * backward side: every gradient equals the float64 restatement of the reference's backward pass
+        evaluated WITH THE DEVICE'S GATES, within tol.
+    The smooth-activation variant of the same shapes (next test) is compared directly and strictly."""
+    with math_mode(ann, mode):
+        ref, tr = make_pair(ann, "784 inputs 2048 relu 2048 relu 10 log_softmax", 1024, learning_rate=0.01,
+                            momentum=0.9, weight_decay=1e-4)
+        tr.set_flag("keep_gradients", 1)
+        for n in tr.weight_names():
+            assert np.array_equal(tr.weights(n), ref.weights[n]), n
+        for step in range(3):
+            x, t = rnd(70 + step, 1024, 784), onehot(80 + step, 1024, 10)
+            w_before = {n: tr.weights(n) for n in tr.weight_names()}
+            l_gpu, rows_gpu = tr.train_step(x, t)
+            l_ref, rows_ref = ref.train_step(x, t)
+            assert abs(l_gpu - l_ref) <= tol * max(1.0, abs(l_ref)), (step, l_gpu, l_ref)
+            assert rel_l2(rows_gpu, rows_ref) < tol, step
+            comps = ref.net.components      # w1 b1 actf1 w2 b2 actf2 w3 b3 actf3
+            gates = []
+            for name, oc in (("actf1", comps[2]), ("actf2", comps[5])):
+                y = tr.component_token(name, "output")
+                assert rel_l2(y, oc.y) < tol, (step, name)
+                flips = (y > 0) != (oc.x > 0)
+                amb = (4e-6 if mode == "fp32" else 4e-3) * float(np.abs(oc.x).std())
+                assert np.all(np.abs(oc.x[flips]) <= amb), (step, name, int(flips.sum()), float(np.abs(oc.x[flips]).max()))
+                assert flips.mean() < (1e-5 if mode == "fp32" else 5e-3), (step, name, int(flips.sum()))
+                gates.append((y > 0).astype(np.float64))
+            g64 = _f64_gradients_with_gates(w_before, x, t, gates[0], gates[1], 1024)
+            for n in tr.weight_names():
+                got = tr.gradients(n).astype(np.float64).reshape(g64[n].shape)
+                if n.startswith("w"):
+                    got = got - 1e-4 * w_before[n]       # the written-back gradient carries + weight_decay * w
+                assert rel_l2(got, g64[n]) < tol, (step, n)
+            # the oracle continues from the DEVICE's state, so that a flipped gate does not compound over the steps
+            for n in tr.weight_names():
+                ref.weights[n][...] = tr.weights(n)
+                ref.optimizer.update[n][...] = tr.updates(n)
+
+
+@pytest.mark.parametrize("mode,tol", [("fp32", 2e-5), ("tf32", TF32_TOL)])
+def test_c2_shapes_smooth_activation_three_steps_vs_oracle(ann, mode, tol):
+    """The C2 shapes with tanh hidden layers (no gate discontinuity): three steps, every gradient, momentum
+    buffer and weight tensor directly against the oracle."""
+    with math_mode(ann, mode):
+        ref, tr = make_pair(ann, "784 inputs 2048 tanh 2048 tanh 10 log_softmax", 1024, learning_rate=0.01,
+                            momentum=0.9, weight_decay=1e-4)
+        tr.set_flag("keep_gradients", 1)
+        for step in range(3):
+            x, t = rnd(70 + step, 1024, 784), onehot(80 + step, 1024, 10)
+            l_gpu, rows_gpu = tr.train_step(x, t)
+            l_ref, rows_ref = ref.train_step(x, t)
+            assert abs(l_gpu - l_ref) <= tol * max(1.0, abs(l_ref)), (step, l_gpu, l_ref)
+            assert rel_l2(rows_gpu, rows_ref) < tol, step
+            for n in tr.weight_names():
+                assert rel_l2(tr.gradients(n), ref.grads[n]) < tol, (step, n)
+                assert rel_l2(tr.updates(n), ref.optimizer.update[n]) < tol, (step, n)
+                # a step moves a weight tensor by ~1e-3 of its norm: the tolerance on the weights themselves
+                # is scaled accordingly so that it still tests the update, not the initialisation
+                assert rel_l2(tr.weights(n), ref.weights[n]) < tol * 1e-2 + 2e-7, (step, n)
+
+
+def test_c2_graph_replay_matches_eager_and_oracle(ann):
+    """The bench runs the captured step graph (stage/step_staged, keep_gradients off): five steps on one
+    staged bunch must land on the oracle's weights -- this is the exact code path of the bench's timed
+    region.  Tolerance on the weight MOVEMENT: 3e-2 for this ReLU net in TF32 mode (gates of units whose
+    pre-activation is within the TF32 rounding of zero flip, see above); 5e-3 with tanh."""
+    for actf, tol in (("relu", 3e-2), ("tanh", 5e-3)):
+        with math_mode(ann, "tf32"):
+            ref, tr = make_pair(ann, "784 inputs 2048 %s 2048 %s 10 log_softmax" % (actf, actf), 1024,
+                                learning_rate=0.01, momentum=0.9, weight_decay=1e-4)
+            x, t = rnd(91, 1024, 784), onehot(92, 1024, 10)
+            w0 = {n: ref.weights[n].copy() for n in ref.weights}
+            tr.loss_reset()
+            for _ in range(5):
+                tr.stage(x, t, 1024)
+                tr.step_staged(1024)
+                ref.train_step(x, t)
+            mean, _ = tr.loss_get()
+            ref_mean, _ = ref.loss.get_accum_loss()
+            assert abs(mean - ref_mean) < 2e-3 * max(1.0, ref_mean)
+            for n in tr.weight_names():
+                assert rel_l2(tr.weights(n) - w0[n], ref.weights[n] - w0[n]) < tol, (actf, n)
+
+
+# ------------------------------------------------------------------ C5: 10 000-class output layer
+@pytest.mark.parametrize("mode,tol", [("fp32", 2e-5), ("tf32", TF32_TOL)])
+def test_c5_full_size_one_step_vs_oracle(ann, mode, tol):
+    """BASELINE configs[4]: 512 -> 10000 log_softmax + MCCE, bunch 4096 (the wide fused softmax/loss
+    kernel, a 4096x10000x512 forward and a 10000x512x4096 weight gradient)."""
+    with math_mode(ann, mode):
+        ref, tr = make_pair(ann, "512 inputs 10000 log_softmax", 4096, learning_rate=0.01, momentum=0.9,
+                            weight_decay=1e-4)
+        tr.set_flag("keep_gradients", 1)
+        x, t = rnd(101, 4096, 512), onehot(102, 4096, 10000)
+        l_gpu, rows_gpu = tr.train_step(x, t)
+        l_ref, rows_ref = ref.train_step(x, t)
+        assert abs(l_gpu - l_ref) <= tol * max(1.0, abs(l_ref))
+        assert rel_l2(rows_gpu, rows_ref) < tol
+        for n in tr.weight_names():
+            assert rel_l2(tr.gradients(n), ref.grads[n]) < tol, n
+            assert rel_l2(tr.updates(n), ref.optimizer.update[n]) < tol, n
+
+
+# ------------------------------------------------------------------ C3: one 8192 x 4096 x 4096 tanh layer
+@pytest.mark.parametrize("mode,tol", [("fp32", F32_TOL), ("tf32", TF32_TOL)])
+def test_c3_layer_all_passes_vs_float64(ann, ops, mode, tol):
+    """BASELINE configs[2] layer shape: forward (+bias +tanh), data gradient (x tanh'), weight gradient
+    (scale, bias column sum) of an 8192 x 4096 -> 4096 layer against float64 numpy on 192 sampled
+    rows of each output (the full float64 products would take minutes on the host)."""
+    M = K = N = None
+    M, K, N = 8192, 4096, 4096
+    X, W, b = rnd(111, M, K), rnd(112, N, K, lo=-0.02, hi=0.02), rnd(113, N)
+    dY = rnd(114, M, N)
+    Yprev = A.antisym_logistic(rnd(115, M, K, lo=-2, hi=2))
+    with math_mode(ann, mode):
+        y = ops.linear_fwd(X, W, b, "tanh")
+        dx = ops.linear_bwd_data(dY, W, "tanh", Yprev)
+        dw, db = ops.linear_bwd_weight(dY, X, scale=1.0 / 64)
+    rows = np.random.RandomState(5).choice(M, 192, replace=False)
+    z = X[rows].astype(np.float64) @ W.astype(np.float64).T + b.astype(np.float64)
+    want_y = 2.0 / (1.0 + np.exp(-z)) - 1.0
+    assert rel_l2(y[rows], want_y) < tol
+    yp = np.clip(Yprev[rows].astype(np.float64), -1 + 1e-6, 1 - 1e-6)
+    want_dx = (dY[rows].astype(np.float64) @ W.astype(np.float64)) * (0.5 * (1.0 - yp * yp))
+    assert rel_l2(dx[rows], want_dx) < tol
+    wr = np.random.RandomState(6).choice(N, 192, replace=False)
+    want_dw = (dY[:, wr].astype(np.float64).T @ X.astype(np.float64)) / 64
+    assert rel_l2(dw[wr], want_dw) < tol
+    assert rel_l2(db, dY.astype(np.float64).sum(axis=0) / 64) < F32_TOL * 10
+
+
+# ------------------------------------------------------------------ C4: the conv net of SURVEY.md 8d
+def c4_gpu(ann):
+    c = ann.components
+    net = c.stack(name="stack")
+    net.push(c.rewrap(size=(1, 28, 28), name="rewrap"),
+             c.convolution(kernel=(1, 5, 5), n=16, name="conv-w1", weights="w1"),
+             c.convolution_bias(n=16, ndims=3, name="conv-b1", weights="b1"),
+             c.actf.relu(name="actf-1"), c.max_pooling(kernel=(1, 2, 2), name="pool-1"),
+             c.convolution(kernel=(16, 5, 5), n=32, name="conv-w2", weights="w2"),
+             c.convolution_bias(n=32, ndims=3, name="conv-b2", weights="b2"),
+             c.actf.relu(name="actf-2"), c.max_pooling(kernel=(1, 2, 2), name="pool-2"),
+             c.flatten(name="flatten"),
+             c.hyperplane(input=512, output=256, name="hyp-1", bias_name="b3", dot_product_name="w3",
+                          bias_weights="b3", dot_product_weights="w3"),
+             c.actf.relu(name="actf-3"),
+             c.hyperplane(input=256, output=10, name="hyp-2", bias_name="b4", dot_product_name="w4",
+                          bias_weights="b4", dot_product_weights="w4"),
+             c.actf.log_softmax(name="actf-4"))
+    return net
+
+
+def c4_oracle():
+    net = A.Stack()
+    net.push(A.Rewrap((1, 28, 28)))
+    net.push(A.Convolution((1, 5, 5), 16, "w1")).push(A.ConvolutionBias(16, "b1")).push(A.Actf("relu"))
+    net.push(A.MaxPooling((1, 2, 2)))
+    net.push(A.Convolution((16, 5, 5), 32, "w2")).push(A.ConvolutionBias(32, "b2")).push(A.Actf("relu"))
+    net.push(A.MaxPooling((1, 2, 2)))
+    net.push(A.Flatten())
+    A.hyperplane(net, 512, 256, "w3", "b3")
+    net.push(A.Actf("relu"))
+    A.hyperplane(net, 256, 10, "w4", "b4")
+    net.push(A.Actf("log_softmax"))
+    net.input_size = 784
+    return net
+
+
+@pytest.mark.parametrize("mode,tol,bunch", [("fp32", 5e-5, 32), ("tf32", 5e-2, 32), ("tf32", 5e-2, 512)])
+def test_c4_conv_net_steps_vs_oracle(ann, mode, tol, bunch):
+    """BASELINE configs[3] architecture (conv 5x5x16 / pool / conv 5x5x32 / pool / 512-256-10 on 1x28x28):
+    two train steps against the oracle, gradients and weights per tensor.  Bunch 32 in both math modes and
+    the full bunch 512 in the tensor-core mode.  The net is all ReLU gates and max-pooling selections, both
+    discontinuous: in TF32 mode units within the TF32 rounding of a tie switch, which moves the gradients by
+    ~1e-2 rel-L2 (the strict TF32 comparison of the convolution contractions themselves, 2e-3, is
+    test_c4_convolution_shapes_tensor_core)."""
+    with math_mode(ann, mode):
+        ref = A.SupervisedTrainer(c4_oracle(), A.MultiClassCrossEntropy(), bunch).build(784)
+        tr = ann.trainable.supervised_trainer(c4_gpu(ann), ann.loss.multi_class_cross_entropy(10), bunch).build(784, 10)
+        tr.set_flag("keep_gradients", 1)
+        for o, v in (("learning_rate", 0.01), ("momentum", 0.9), ("weight_decay", 1e-4)):
+            ref.set_option(o, v)
+            tr.set_option(o, v)
+        ref.randomize_weights(random=MTRand(1234), inf=-1, sup=1, use_fanin=True, use_fanout=True)
+        for n in tr.weight_names():
+            tr.set_weights(n, ref.weights[n])
+        for step in range(2):
+            x, t = rnd(120 + step, bunch, 784, lo=0.0, hi=1.0), onehot(130 + step, bunch, 10)
+            l_gpu, _ = tr.train_step(x, t)
+            l_ref, _ = ref.train_step(x, t)
+            assert abs(l_gpu - l_ref) < tol * max(1.0, abs(l_ref)), (step, l_gpu, l_ref)
+            for n in tr.weight_names():
+                assert rel_l2(tr.gradients(n), ref.grads[n]) < tol, (step, n)
+                assert rel_l2(tr.weights(n), ref.weights[n]) < tol, (step, n)
+            for n in tr.weight_names():     # continue from the device's state: switched gates must not compound
+                ref.weights[n][...] = tr.weights(n)
+                ref.optimizer.update[n][...] = tr.updates(n)
+
+
+@pytest.mark.parametrize("B,C,H,W,n,k", [(512, 1, 28, 28, 16, 5), (512, 16, 12, 12, 32, 5)])
+def test_c4_convolution_shapes_tensor_core(ann, ops, B, C, H, W, n, k):
+    """The two convolutions of C4 at full bunch in TF32 mode (implicit GEMM on tcgen05), every pass
+    against the oracle's per-pixel GEMM restatement."""
+    x = rnd(140, B, C, H, W)
+    w = rnd(141, n, C * k * k, lo=-0.2, hi=0.2)
+    bias = rnd(142, n)
+    conv = A.Convolution((C, k, k), n, "w")
+    weights = {}
+    conv.build(0, weights)
+    weights["w"][...] = w
+    y_ref = conv.forward(x)
+    dy = rnd(143, *y_ref.shape)
+    dx_ref = conv.backprop(dy)
+    g, c = {}, {}
+    conv.compute_gradients(g, c)
+    with math_mode(ann, "tf32"):
+        y = ops.conv2d_fwd(x, w, (k, k), (1, 1), bias=bias, act="relu")
+        dx = ops.conv2d_bwd_data(dy, w, x.shape, (k, k), (1, 1))
+        dw, db = ops.conv2d_bwd_weight(dy, x, (k, k), (1, 1), scale=0.125)
+    assert rel_l2(y, A.relu(y_ref + bias[None, :, None, None])) < TF32_TOL
+    assert rel_l2(dx, dx_ref) < TF32_TOL
+    assert rel_l2(dw, 0.125 * g["w"]) < TF32_TOL
+    assert rel_l2(db, 0.125 * dy.astype(np.float64).sum(axis=(0, 2, 3))) < F32_TOL * 10
+
+
+# ------------------------------------------------------------------ exports no other test reaches
+def test_gemv_reference_cases(ops):
+    """packages/basics/matrix/test/test_gemv.lua: exact integer cases, both transposes."""
+    Amat = np.array([[1, 2, 3], [4, 5, 6]], np.float32)
+    assert np.array_equal(ops.sgemv(0, 1.0, Amat, [3, 1, 9]), [32, 71])
+    assert np.array_equal(ops.sgemv(1, 1.0, Amat, [9, 7]), [37, 53, 69])
+    assert np.array_equal(ops.sgemv(0, 1.0, np.ascontiguousarray(Amat.T), [9, 7]), [37, 53, 69])
+    assert np.array_equal(ops.sgemv(1, 1.0, np.ascontiguousarray(Amat.T), [3, 1, 9]), [32, 71])
+    # alpha / beta / strided vectors (the `inc` arguments of doGemv, cblas_headers.h:300-330)
+    Ar, x = rnd(150, 37, 53), rnd(151, 53 * 2)
+    y0 = rnd(152, 37 * 3)
+    got = ops.sgemv(0, 0.5, Ar, x, beta=2.0, y0=y0, incx=2, incy=3)
+    want = y0.astype(np.float64).copy()
+    want[::3] = 2.0 * y0[::3] + 0.5 * (Ar.astype(np.float64) @ x[::2])
+    assert rel_l2(got, want) < F32_TOL
+    got_t = ops.sgemv(1, 1.0, Ar, rnd(153, 37))
+    assert rel_l2(got_t, Ar.astype(np.float64).T @ rnd(153, 37)) < F32_TOL
+
+
+def test_ger_reference_cases(ops):
+    """packages/basics/matrix/test/test_ger.lua: rank-1 updates, exact."""
+    x, y = np.array([3, 1, 9], np.float32), np.array([9, 7, 10], np.float32)
+    z = np.zeros((3, 3), np.float32)
+    assert np.array_equal(ops.sger(1.0, x, y, z), np.outer(x, y))
+    assert np.array_equal(ops.sger(1.0, y, x, z), np.outer(y, x))
+    A0, xs, ys = rnd(154, 40, 33), rnd(155, 40 * 2), rnd(156, 33)
+    got = ops.sger(-0.25, xs, ys, A0, incx=2)
+    assert rel_l2(got, A0.astype(np.float64) - 0.25 * np.outer(xs[::2], ys)) < F32_TOL
+
+
+@pytest.mark.parametrize("n", [1, 5, 1000, 4099, 1 << 20])
+def test_level1_maps_and_reductions(ops, n):
+    """axpy / scal / copy / cmul / sum / nrm2 (axpy.cu:42, scal.cu:38, copy.cu:43, matCmul, matSum, nrm2.h:131)
+    incl. lengths that are not a multiple of the float4 vector width."""
+    x, y = rnd(160, n), rnd(161, n)
+    assert np.array_equal(ops.saxpy(0.5, x, y), (np.float32(0.5) * x + y).astype(np.float32)) or \
+        np.allclose(ops.saxpy(0.5, x, y), 0.5 * x.astype(np.float64) + y, rtol=1e-6, atol=1e-7)
+    assert np.array_equal(ops.sscal(-3.0, x), np.float32(-3.0) * x)
+    assert np.array_equal(ops.scopy(x), x)
+    assert np.array_equal(ops.cmul(x, y), x * y)
+    s = float(x.astype(np.float64).sum())
+    assert abs(ops.ssum(x) - s) <= 1e-5 * max(1.0, np.abs(x).astype(np.float64).sum())
+    want = float((x.astype(np.float64) ** 2).sum() + (y.astype(np.float64) ** 2).sum())
+    assert abs(ops.nrm2sq([x, y]) - want) <= 1e-5 * want
+
+
+def test_bias_forward_kernels(ops):
+    """b200_bias_fwd (bias_component.cc:46-73) and b200_conv_bias_fwd (convolution_bias_component.cc:120-176)
+    called directly (inside a stack they are fused into the contraction epilogue)."""
+    x, b = rnd(170, 33, 77), rnd(171, 77)
+    assert np.array_equal(ops.bias_fwd(x, b), x + b[None, :])
+    xc, bc = rnd(172, 5, 7, 6, 9), rnd(173, 7)
+    assert np.array_equal(ops.conv_bias_fwd(xc, bc), xc + bc[None, :, None, None])
+
+
+def test_gather_rows(ops):
+    data = rnd(174, 100, 36)
+    idx = np.random.RandomState(7).permutation(100)[:64]
+    assert np.array_equal(ops.gather_rows(data, idx), data[idx])
+    data3 = rnd(175, 50, 7)      # row length not a multiple of 4: scalar path
+    assert np.array_equal(ops.gather_rows(data3, idx[:20] % 50), data3[idx[:20] % 50])
+
+
+def test_calculate_and_component_tokens(ann):
+    """trainer:calculate (supervised.lua:1236-1245) and get_input / get_output / get_error_input /
+    get_error_output of named components (bind_ann_base.lua.cc:392-565) with fusion off, against the
+    oracle's per-component tensors."""
+    topo = "20 inputs 16 tanh 12 logistic 5 log_softmax"
+    ref_loss = A.MultiClassCrossEntropy()
+    ref = A.SupervisedTrainer(A.mlp_all_all(topo), ref_loss, 9).build()
+    tr = ann.trainable.supervised_trainer(ann.mlp.all_all.generate(topo), ann.loss.multi_class_cross_entropy(), 9).build()
+    ref.randomize_weights(random=MTRand(99), inf=-1, sup=1, use_fanin=True)
+    tr.randomize_weights(random=ann.random(99), inf=-1, sup=1, use_fanin=True)
+    x, t = rnd(180, 9, 20), onehot(181, 9, 5)
+    y = tr.calculate(x)
+    assert rel_l2(y, ref.net.forward(x)) < F32_TOL
+    assert np.allclose(np.exp(y.astype(np.float64)).sum(axis=1), 1.0, atol=1e-5)
+    tr.set_flag("fuse", 0)
+    tr.set_flag("cuda_graph", 0)
+    tr.train_step(x, t)
+    out = ref.net.forward(x, True)
+    ref.net.backprop(ref_loss.gradient(out, t))
+    comps = ref.net.components          # w1 b1 actf1 w2 b2 actf2 w3 b3 actf3
+    assert rel_l2(tr.component_token("w1", "input"), x) == 0.0
+    assert rel_l2(tr.component_token("actf1", "output"), comps[2].y) < F32_TOL
+    assert rel_l2(tr.component_token("actf2", "output"), comps[5].y) < F32_TOL
+    assert rel_l2(tr.component_token("w3", "error_input"), comps[6].dy) < F32_TOL
+    assert rel_l2(tr.component_token("w2", "error_input"), comps[3].dy) < 2e-5
+    assert tr.component_token("actf3", "output").shape == (9, 5)
+    with pytest.raises(ann.B200Error):
+        tr.component_token("no_such_component", "output")
