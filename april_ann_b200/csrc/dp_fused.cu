@@ -13,8 +13,9 @@
 // rank drops to 1/N.
 //
 // Cross-GPU ordering uses one 64-bit tag per (bucket, rank) in every rank's flag block, written with
-// release.sys and polled with acquire.sys; the tag is the step number (device step counter + 1), so
-// nothing is ever reset and the kernel can live in a replayed CUDA graph:
+// release.sys and polled with acquire.sys; the tag is the replica group's epoch + 1 (count_dev[2], advanced by
+// b200_dp_wait at the end of every step and never set back -- unlike the optimizer's step count count_dev[0],
+// which a checkpoint restore rewrites), so nothing is ever reset and the kernel can live in a replayed CUDA graph:
 //   READY[b][r] = s   rank r's gradients of bucket b are final for step s AND r no longer reads the
 //                     bucket's weights in step s (its data gradients are done) -> peers may read r's
 //                     gradients and overwrite r's weights
@@ -67,7 +68,7 @@ dp_fused_update_kernel(const b200_dp_group grp, const b200_sgd_tensor *__restric
                        int64_t *count_dev, int bucket, int dbg) {
   const int rank = grp.rank, nranks = grp.nranks;
   const int64_t count = *reinterpret_cast<volatile int64_t *>(count_dev);
-  const long long tag = (long long)count + 1;
+  const long long tag = (long long)*reinterpret_cast<volatile int64_t *>(count_dev + 2) + 1;   // replica-group epoch, not the optimizer's count
   if (blockIdx.x == 0 && threadIdx.x == 0) *dbg_slot(grp.flags[rank], bucket, 0) = gtime();
 
   // Shard q of a tensor = float4 [q*per, (q+1)*per) of its slot; the shards of all tensors of the bucket that
@@ -212,7 +213,7 @@ dp_fused_update_kernel(const b200_dp_group grp, const b200_sgd_tensor *__restric
 // A bucket is a contiguous range of the arenas; rank q owns the q-th of nranks slices of it (128-float
 // granules), so every copy is one contiguous block.
 __global__ void dp_signal_kernel(const b200_dp_group grp, int bucket, int done, const int64_t *count_dev) {
-  const long long tag = (long long)*count_dev + 1;
+  const long long tag = (long long)count_dev[2] + 1;
   if (threadIdx.x < grp.nranks) {
     long long *f = done ? done_slot(grp.flags[threadIdx.x], bucket, grp.rank) : ready_slot(grp.flags[threadIdx.x], bucket, grp.rank);
     __threadfence_system();
@@ -226,7 +227,7 @@ dp_shard_update_kernel(const b200_dp_group grp, const b200_sgd_tensor *__restric
                        const int64_t *count_dev, int bucket, unsigned long long lo4, unsigned long long hi4) {
   const int rank = grp.rank, nranks = grp.nranks;
   const int64_t count = *count_dev;
-  const long long tag = (long long)count + 1;
+  const long long tag = (long long)count_dev[2] + 1;
   if (blockIdx.x == 0 && threadIdx.x == 0) *dbg_slot(grp.flags[rank], bucket, 0) = gtime();
   constexpr int MAXT = 32;
   __shared__ unsigned long long s_beg4[MAXT];       // first float4 of every tensor's slot inside the arenas
@@ -307,12 +308,17 @@ dp_shard_update_kernel(const b200_dp_group grp, const b200_sgd_tensor *__restric
   if (blockIdx.x == 0 && threadIdx.x == 0) *dbg_slot(grp.flags[rank], bucket, 2) = gtime();
 }
 
-__global__ void dp_wait_kernel(const b200_dp_group grp, int nbuckets, const int64_t *count_dev) {
-  const long long tag = (long long)*count_dev + 1;
+// Also closes the step for the replica group: the epoch (count_dev[2]) the tags are derived from advances here,
+// once every shard of every bucket has landed.  The epoch is separate from the optimizer's step count
+// (count_dev[0], which a checkpoint restore may set back): tags must never decrease.
+__global__ void dp_wait_kernel(const b200_dp_group grp, int nbuckets, int64_t *count_dev) {
+  const long long tag = (long long)count_dev[2] + 1;
   for (int i = threadIdx.x; i < nbuckets * grp.nranks; i += blockDim.x) {
     const long long *f = done_slot(grp.flags[grp.rank], i / grp.nranks, i % grp.nranks);
     while (ld_acquire_sys(f) < tag) { }
   }
+  __syncthreads();
+  if (threadIdx.x == 0) count_dev[2] = tag;
 }
 
 }  // namespace
@@ -434,7 +440,7 @@ extern "C" int b200_dp_fused_update(b200_ctx *ctx, const b200_dp_group *grp, int
   return B200_OK;
 }
 
-extern "C" int b200_dp_wait(b200_ctx *ctx, const b200_dp_group *grp, int nbuckets, const int64_t *count_dev) {
+extern "C" int b200_dp_wait(b200_ctx *ctx, const b200_dp_group *grp, int nbuckets, int64_t *count_dev) {
   B200_ENTER(ctx);
   ARG_CHECK(ctx && grp && count_dev, "NULL pointer");
   ARG_CHECK(nbuckets >= 0 && nbuckets <= DP_MAX_BUCKETS, "bucket count out of range");

@@ -170,9 +170,10 @@ SupervisedTrainer::SupervisedTrainer(b200_ctx *ctx, const std::shared_ptr<StackA
   if (const char *e = getenv("B200_SGD_AS_READY")) sgd_as_ready = atoi(e) != 0;
   if (const char *e = getenv("B200_CONCURRENT_BWD")) net->contraction_mode = atoi(e);
   void *p;
-  check(b200_malloc(ctx, &p, 2 * sizeof(int64_t)));
+  // [0] optimizer step count, [1] ticket, [2] replica-group epoch, [3] reserved (include/b200ann.h, b200_dp_wait)
+  check(b200_malloc(ctx, &p, 4 * sizeof(int64_t)));
   count_dev = (int64_t *)p;
-  check(b200_memset_zero(ctx, count_dev, 2 * sizeof(int64_t)));
+  check(b200_memset_zero(ctx, count_dev, 4 * sizeof(int64_t)));
 }
 SupervisedTrainer::~SupervisedTrainer() {
   b200_sync(ctx);

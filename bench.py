@@ -228,7 +228,7 @@ def parity_phase(args, ann, tr, ctx, dist, rank, world):
     (seeded by rank and step) through the data-parallel path that was just timed.  Rank 0: the oracle's k steps
     on the concatenated global bunch from the same weights; compares the weight MOVEMENT and the last loss."""
     name = args.config
-    k, pb = PARITY_STEPS[name], PARITY_BUNCH[name]
+    k, pb = int(os.environ.get("B200_PARITY_STEPS", PARITY_STEPS[name])), PARITY_BUNCH[name]
     names = tr.weight_names()
     rng = np.random.RandomState(4321)          # same stream on every rank -> identical replicas
     w0 = {}

@@ -281,7 +281,9 @@ size_t b200_dp_flags_bytes(void);
 size_t b200_dp_debug_offset(void);   /* bring-up: 4 globaltimer stamps per bucket live behind the tags */
 int b200_dp_fused_update(b200_ctx *ctx, const b200_dp_group *grp, int ntensors, const b200_sgd_tensor *tensors_dev,
                          const b200_sgd_tensor *tensors_host, double decay, int64_t *count_dev, int bucket);
-int b200_dp_wait(b200_ctx *ctx, const b200_dp_group *grp, int nbuckets, const int64_t *count_dev);
+/* count_dev: FOUR int64 on the device: [0] optimizer step count (lr decay), [1] ticket word of the update kernels,
+ * [2] replica-group epoch (the cross-GPU tags are epoch + 1; advanced by b200_dp_wait, never set back), [3] reserved */
+int b200_dp_wait(b200_ctx *ctx, const b200_dp_group *grp, int nbuckets, int64_t *count_dev);
 
 /* ------------------------------------------------------------------ convolution / pooling
  * replaces ConvolutionANNComponent, ConvolutionBiasANNComponent, MaxPoolingANNComponent
