@@ -90,6 +90,25 @@ extern "C" int b200_linear_bwd_data(b200_ctx *ctx, int M, int N, int K, const fl
   return gemm_dispatch(ctx, 0, 0, M, K, N, dY, lddy, W, ldw, dX, lddx, ep);
 }
 
+// dX += ( dY . W ) (.) act'(Yprev): the accumulate form.  With the tensor-core path and a ReLU (or no) derivative the
+// tiles are ADDED into dX with TMA reduce-add stores, so split-K needs no exchange between CTAs; the caller
+// provides a zeroed (or partially accumulated) dX.
+extern "C" int b200_linear_bwd_data_acc(b200_ctx *ctx, int M, int N, int K, const float *dY, int lddy, const float *W,
+                                        int ldw, int act_prev, const float *Yprev, int ldyp, float *dX, int lddx) {
+  B200_ENTER(ctx);
+  ARG_CHECK(ctx && dY && W && dX, "NULL pointer");
+  const bool has_prev = (act_prev == B200_ACT_LOGISTIC || act_prev == B200_ACT_TANH || act_prev == B200_ACT_RELU);
+  if (has_prev) ARG_CHECK(Yprev, "Yprev is required when act_prev is set");
+  GemmEpilogue ep;
+  ep.beta = 1.0f;
+  if (has_prev) {
+    ep.dact = act_prev;
+    ep.dsrc = Yprev;
+    ep.ld_dsrc = ldyp;
+  }
+  return gemm_dispatch(ctx, 0, 0, M, K, N, dY, lddy, W, ldw, dX, lddx, ep);
+}
+
 extern "C" int b200_linear_bwd_weight(b200_ctx *ctx, int M, int N, int K, const float *dY, int lddy,
                                       const float *X, int ldx, float scale, float beta, float *dW,
                                       int lddw, float *db) {

@@ -32,6 +32,7 @@ struct b200_ctx {
   cudaStream_t comm_stream = nullptr;
   cudaEvent_t ev_compute = nullptr, ev_comm = nullptr;
   cudaEvent_t ev_bucket[16] = {};        // completion of the async gradient buckets
+  cudaEvent_t ev_fence[8] = {};          // b200_fence_record / b200_fence_wait
   uint64_t launches = 0;
   // caching pool: size -> free blocks ; ptr -> size for live blocks
   std::multimap<size_t, void *> free_blocks;
@@ -180,6 +181,26 @@ int skinny_bwd_data(b200_ctx *ctx, int M, int N, int K, const float *dY, int ldd
 int skinny_bwd_weight(b200_ctx *ctx, int M, int N, int K, const float *dY, int lddy, const float *X, int ldx, float scale,
                       float beta, float *dW, int lddw, float *db);
 int colsum_scaled(b200_ctx *ctx, int M, int N, const float *dy, int ld, float scale, float beta, float *out);
+
+// Programmatic dependent launch: a kernel launched with launch_pdl may start while its predecessor on the stream is
+// still draining; it must call pdl_wait() before it touches anything the predecessor wrote, and may call
+// pdl_launch_dependents() once the next kernel's prologue can no longer get in its way.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <class... KArgs, class... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

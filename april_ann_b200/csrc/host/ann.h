@@ -135,6 +135,9 @@ class DotProductANNComponent : public ANNComponent {
   const char *kind() const override { return "dot_product"; }
   int sharedCountContribution() const override { return 1; }
   MatrixPtr weights_matrix;
+  // tensor-core mode: the data gradient of this layer is ADDED into a buffer that was allocated and zeroed during
+  // the forward pass (on a side branch), so that the contraction can split K without an exchange
+  MatrixPtr dx_zeroed;
 };
 
 class BiasANNComponent : public ANNComponent {
@@ -277,6 +280,7 @@ class StackANNComponent : public ANNComponent {
   void setContext(b200_ctx *c) override;
   std::vector<ComponentPtr> components;   // as pushed (hyperplanes are nested stacks)
   bool fuse = true;                       // false: run every component separately (all tokens observable)
+  bool zero_accumulate = false;           // trainer: data gradients accumulate into buffers zeroed during the forward pass
   bool skip_input_gradient = false;       // trainer: the network-input gradient is never used
   ANNComponent *lastComponent();
   // set by the trainer when the loss kernel already produced d(loss)/d(pre-activation)
@@ -433,6 +437,10 @@ class SupervisedTrainer {
   bool use_branches = true;       // single replica: weight gradients / updates / statistics on side branches
   bool sgd_as_ready = true;       // single replica: update each big tensor as soon as it is ready (false: one launch at the end)
   bool fuse_output_layer = true;  // <=16-class output layer + log_softmax + MCCE + data gradient in one launch
+  // tensor-core mode: zero the big gradient tensors under the forward pass and let the contractions ACCUMULATE
+  // (TMA reduce-add stores, exchange-free split-K).  Measured on C2: the contraction alone gains 8 % (18.5 vs
+  // 20.0 us), but the 30 MB of memsets under the forward pass cost more than that (step 118 -> 125 us): off.
+  bool zero_accumulate = false;
   MatrixDict weights_table, grads, updates;
   std::vector<std::string> weights_order;   // sorted names (initialisation / API order)
   std::vector<std::string> arena_order;     // layout of the flat arenas: reverse layer order

@@ -168,6 +168,7 @@ int b200h_trainer_set_flag(b200_trainer *t, const char *flag, int value) {
     if (f == "fuse") t->net->fuse = value != 0;
     else if (f == "cuda_graph") t->t->use_cuda_graph = value != 0;
     else if (f == "branches") t->t->use_branches = value != 0;
+    else if (f == "zero_accumulate") t->t->zero_accumulate = value != 0;
     else if (f == "fuse_output_layer") t->t->fuse_output_layer = value != 0;
     else if (f == "dp_fused") {   // 0: back to the NCCL all-reduce path (1 needs a connected replica group)
       if (value != 0 && t->t->dp_group.nranks < 2) throw Error(B200_ERR_BAD_ARG, "dp_fused needs b200h_trainer_dp_connect");

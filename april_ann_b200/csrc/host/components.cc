@@ -555,6 +555,23 @@ MatrixPtr StackANNComponent::doForward(const MatrixPtr &in, bool during_training
         if (b) { b->input.reset(); b->output.reset(); }
         if (a) { a->input.reset(); a->output = y; }
         (a ? (ANNComponent *)a : (b ? (ANNComponent *)b : (ANNComponent *)dot))->output = y;
+        // the buffer this layer's data gradient will be accumulated into: allocated and zeroed now, on the
+        // weight-gradient branch, far ahead of the backward pass (tensor-core mode, big layers, and only when the
+        // derivative of the layer below is a ReLU gate or absent: those epilogues distribute over partial sums)
+        dot->dx_zeroed.reset();
+        if (zero_accumulate && during_training && use_branches && N > 16 && !(i == 0 && skip_input_gradient)) {
+          int mode = B200_MATH_FP32;
+          check(b200_get_math_mode(ctx, &mode));
+          ActivationFunctionANNComponent *pa = (i >= 1) ? dynamic_cast<ActivationFunctionANNComponent *>(flat[i - 1]) : nullptr;
+          const bool gate_ok = !pa || !pa->elementwise() || pa->act == B200_ACT_RELU || pa->act == B200_ACT_LINEAR;
+          if (mode == B200_MATH_TF32 && gate_ok && (long)bunch * K >= 128 * 256) {
+            dot->dx_zeroed = Matrix::create(ctx, dims2(bunch, K));
+            check(b200_branch_begin(ctx, 2));
+            dot->dx_zeroed->zeros();
+            check(b200_fence_record(ctx, (int)(i & 7)));   // (ids may alias in deep nets: a later mark on the same branch implies the earlier one)
+            check(b200_branch_end(ctx));
+          }
+        }
         cur = y;
         i = ai + (a ? 1 : 0);
         continue;
@@ -671,6 +688,12 @@ MatrixPtr StackANNComponent::doBackprop(const MatrixPtr &err) {
         MatrixPtr dx;
         if (dot == precomputed_for && precomputed_dx) {
           dx = precomputed_dx;   // produced by the fused output-layer launch (same pa decision)
+        } else if (dot->dx_zeroed && dot->dx_zeroed->rows() == bunch) {
+          dx = dot->dx_zeroed;   // zeroed during the forward pass on branch 2
+          dot->dx_zeroed.reset();
+          check(b200_fence_wait(ctx, i & 7));
+          check(b200_linear_bwd_data_acc(ctx, bunch, N, K, cur->data, N, dot->weights_matrix->data, K,
+                                         pa ? pa->act : B200_ACT_NONE, pa ? pa->output->data : nullptr, K, dx->data, K));
         } else {
           dx = Matrix::create(ctx, dims2(bunch, K));
           check(b200_linear_bwd_data(ctx, bunch, N, K, cur->data, N, dot->weights_matrix->data, K,

@@ -169,6 +169,7 @@ SupervisedTrainer::SupervisedTrainer(b200_ctx *ctx, const std::shared_ptr<StackA
   if (const char *e = getenv("B200_FUSE_OUTPUT")) fuse_output_layer = atoi(e) != 0;
   if (const char *e = getenv("B200_SGD_AS_READY")) sgd_as_ready = atoi(e) != 0;
   if (const char *e = getenv("B200_CONCURRENT_BWD")) net->contraction_mode = atoi(e);
+  if (const char *e = getenv("B200_ZERO_ACC")) zero_accumulate = atoi(e) != 0;
   void *p;
   // [0] optimizer step count, [1] ticket, [2] replica-group epoch, [3] reserved (include/b200ann.h, b200_dp_wait)
   check(b200_malloc(ctx, &p, 4 * sizeof(int64_t)));
@@ -529,6 +530,28 @@ void SupervisedTrainer::runStep(const MatrixPtr &x, const MatrixPtr &t, int glob
     check(b200_optimizer_lookahead(ctx, (int)opt_host.size(), opt_dev, opt_host.data()));
   net->reset();
   for (auto &kv : grads) kv.second->fresh = true;
+  {
+    // Tensor-core mode: the gradients of the big contractions are zeroed now, on the weight-gradient branch and
+    // under the forward pass, and the contractions ACCUMULATE into them (the reference's own order:
+    // md.zeros(grads) then beta = 1 GEMMs, supervised.lua:792-794) -- with beta == 1 the tensor-core kernel adds
+    // its tiles with TMA reduce-add stores and may split K without any exchange between CTAs.
+    int mode = B200_MATH_FP32;
+    check(b200_get_math_mode(ctx, &mode));
+    net->zero_accumulate = zero_accumulate;
+    if (zero_accumulate && mode == B200_MATH_TF32 && use_branches && net->fuse) {
+      bool any = false;
+      for (size_t i = 0; i < arena_order.size(); ++i) {
+        if (!tensor_heavy[i]) continue;
+        MatrixPtr g = grads[arena_order[i]];
+        if (!any) check(b200_branch_begin(ctx, 2));
+        any = true;
+        g->zeros();
+        g->fresh = false;
+      }
+      if (any) check(b200_branch_end(ctx));
+    }
+  }
+  net->use_branches = use_branches;   // (the forward pass zeroes the data-gradient buffers on a branch as well)
   auto *last = dynamic_cast<ActivationFunctionANNComponent *>(net->lastComponent());
   const bool fused_loss =
       net->fuse && last && last->act == B200_ACT_LOG_SOFTMAX && loss.kind == LOSS_MULTI_CLASS_CROSS_ENTROPY;

@@ -79,6 +79,7 @@ extern "C" int b200_create(int device, b200_ctx **out) {
   CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_compute, cudaEventDisableTiming));
   CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_comm, cudaEventDisableTiming));
   for (auto &e : ctx->ev_bucket) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  for (auto &e : ctx->ev_fence) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   *out = ctx;
   return B200_OK;
 }
@@ -116,6 +117,7 @@ extern "C" int b200_destroy(b200_ctx *ctx) {
   cudaEventDestroy(ctx->ev_compute);
   cudaEventDestroy(ctx->ev_comm);
   for (auto &e : ctx->ev_bucket) if (e) cudaEventDestroy(e);
+  for (auto &e : ctx->ev_fence) if (e) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->main_stream);
   cudaStreamDestroy(ctx->comm_stream);
   delete ctx;
@@ -199,6 +201,21 @@ extern "C" int b200_branch_join_all(b200_ctx *ctx) {
   std::lock_guard<std::mutex> lk(ctx->mu);
   for (auto &kv : ctx->deferred_free) ctx->free_blocks.emplace(kv.first, kv.second);
   ctx->deferred_free.clear();
+  return B200_OK;
+}
+// A point-to-point edge between the streams of a step: b200_fence_record(id) marks what the CURRENT stream (main or
+// the open branch) holds now, b200_fence_wait(id) makes the current stream wait for exactly that -- unlike
+// b200_branch_wait, which waits for everything the branch holds at the time of the call.
+extern "C" int b200_fence_record(b200_ctx *ctx, int id) {
+  B200_ENTER(ctx);
+  ARG_CHECK(ctx && id >= 0 && id < 8, "fence id in [0, 8)");
+  CUDA_TRY(cudaEventRecord(ctx->ev_fence[id], ctx->stream));
+  return B200_OK;
+}
+extern "C" int b200_fence_wait(b200_ctx *ctx, int id) {
+  B200_ENTER(ctx);
+  ARG_CHECK(ctx && id >= 0 && id < 8, "fence id in [0, 8)");
+  CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_fence[id], 0));
   return B200_OK;
 }
 extern "C" int b200_set_sm_budget(b200_ctx *ctx, int sms) {

@@ -176,6 +176,8 @@ __global__ void __launch_bounds__(256, (R <= 4) ? 2 : 1) output_layer_fused_kern
   __shared__ float sg[R][NT];          // logits, then the gradient rows
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int m0 = blockIdx.x * R;
+  pdl_wait();                  // X is the previous kernel's output
+  pdl_launch_dependents();     // the data-gradient contraction that follows may set itself up on the idle SMs
   {
     float acc[V];
 #pragma unroll
@@ -643,8 +645,8 @@ extern "C" int b200_output_layer_fused(b200_ctx *ctx, int M, int N, int K, const
   constexpr int R = 8;
   const int grid = (M + R - 1) / R;
   NT_DISPATCH(N, {
-    output_layer_fused_kernel<NT, R><<<grid, 256, 0, ctx->stream>>>(M, N, K, X, ldx, W, ldw, bias, target, logits, logp,
-                                                                  loss_rows, grad, dact, dX, lddx);
+    CUDA_TRY(launch_pdl(output_layer_fused_kernel<NT, R>, dim3(grid), dim3(256), 0, ctx->stream, M, N, K, X, ldx, W, ldw, bias,
+                        target, logits, logp, loss_rows, grad, dact, dX, lddx));
   });
   LAUNCH_CHECK(ctx);
   return B200_OK;

@@ -98,6 +98,10 @@ int b200_branch_end(b200_ctx *ctx);
 int b200_branch_wait(b200_ctx *ctx, int branch);
 int b200_branch_join_all(b200_ctx *ctx);
 int b200_set_sm_budget(b200_ctx *ctx, int sms);
+/* point-to-point edge: record marks what the current stream (main or the open branch) holds now, wait makes the
+ * current stream wait for exactly that; id in [0, 8) */
+int b200_fence_record(b200_ctx *ctx, int id);
+int b200_fence_wait(b200_ctx *ctx, int id);
 /* CUDA-event timing on the compute stream (bench / roofline) */
 int b200_event_create(void **ev);
 int b200_event_destroy(void *ev);
@@ -141,6 +145,12 @@ int b200_linear_fwd(b200_ctx *ctx, int M, int N, int K, const float *X, int ldx,
 int b200_linear_bwd_data(b200_ctx *ctx, int M, int N, int K, const float *dY, int lddy,
                          const float *W, int ldw, int act_prev, const float *Yprev, int ldyp,
                          float *dX, int lddx);
+/* dX += (dY . W) (.) act'(Yprev): accumulate form of bwd_data (the reference's beta = 1 GEMM into a zeroed matrix,
+ * convolution_component.cc:265).  On the tensor-core path the tiles are added with TMA reduce-add stores, which
+ * makes split-K exchange-free. */
+int b200_linear_bwd_data_acc(b200_ctx *ctx, int M, int N, int K, const float *dY, int lddy,
+                             const float *W, int ldw, int act_prev, const float *Yprev, int ldyp,
+                             float *dX, int lddx);
 int b200_linear_bwd_weight(b200_ctx *ctx, int M, int N, int K, const float *dY, int lddy,
                            const float *X, int ldx, float scale, float beta,
                            float *dW, int lddw, float *db);

@@ -29,6 +29,7 @@ for a in sys.argv[1:]:
     st = DeviceArray(ctx, (148 * 32,), np.int64)
 
     op = v[8] if len(v) > 8 else 0
+    beta = float(v[9]) if len(v) > 9 else 0.0
     Yp = DeviceArray.from_numpy(ctx, rng.uniform(-1, 1, (M, N)).astype(np.float32)) if op else None
 
     def launch():
@@ -37,7 +38,7 @@ for a in sys.argv[1:]:
                                            C.c_int(3), Yp.ptr, C.c_int(N), Cm.ptr, C.c_int(N)))
             return
         check(lib.b200_sgemm(ctx.h, C.c_int(ta), C.c_int(tb), C.c_int(M), C.c_int(N), C.c_int(K), C.c_float(1.0),
-                             A.ptr, C.c_int(M if ta else K), B.ptr, C.c_int(K if tb else N), C.c_float(0.0), Cm.ptr, C.c_int(N)))
+                             A.ptr, C.c_int(M if ta else K), B.ptr, C.c_int(K if tb else N), C.c_float(beta), Cm.ptr, C.c_int(N)))
     for _ in range(3):
         launch()
     st.zero()

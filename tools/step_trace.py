@@ -1,4 +1,4 @@
-"""Timeline of one replayed C2 training step (GPU box): kernel start / duration / stream from CUPTI
+"""Timeline of one replayed training step (CFGNAME=C1..C5, default C2) (GPU box): kernel start / duration / stream from CUPTI
 through torch.profiler (the kernels are this library's; torch only hosts the profiler).
 
     python tools/step_trace.py [steps]
@@ -16,7 +16,7 @@ import torch  # noqa: E402
 from torch.profiler import ProfilerActivity, profile  # noqa: E402
 
 import april_ann_b200 as ann  # noqa: E402
-import bench  # noqa: E402
+from april_ann_b200 import configs as CFG  # noqa: E402
 
 rank = int(os.environ.get("RANK", "0"))
 world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -25,14 +25,9 @@ torch.cuda.set_device(local_rank)
 torch.zeros(1, device="cuda")
 ctx = ann.get_context(local_rank)
 ctx.set_math_mode(ann.MATH_TF32)
-topo = os.environ.get("TOPOLOGY", bench.TOPOLOGY)
-bunch = int(os.environ.get("BUNCH", bench.BUNCH))
-tr = ann.trainable.supervised_trainer(ann.mlp.all_all.generate(topo), ann.loss.multi_class_cross_entropy(), bunch, ctx=ctx)
-tr.build()
-tr.set_option("learning_rate", 0.01)
-tr.set_option("momentum", 0.9)
-tr.set_option("weight_decay", 1e-4)
-tr.set_layerwise_option("b.", "weight_decay", 0)
+name = os.environ.get("CFGNAME", "C2")
+bunch = CFG.CONFIGS[name]["bunch"]
+tr = CFG.build_trainer(ann, name, ctx=ctx)
 tr.randomize_weights(random=ann.random(1234), inf=-1, sup=1, use_fanin=True, use_fanout=True)
 if world > 1:   # replica group: python -m torch.distributed.run --nproc-per-node N tools/step_trace.py
     import torch.distributed as dist
@@ -40,11 +35,7 @@ if world > 1:   # replica group: python -m torch.distributed.run --nproc-per-nod
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     dist.init_process_group(backend="gloo")
     init_data_parallel(tr, dist)
-sizes = [int(v) for v in topo.split() if v.isdigit()]
-rng = np.random.RandomState(1)
-x = rng.uniform(-1, 1, (bunch, sizes[0])).astype(np.float32)
-t = np.zeros((bunch, sizes[-1]), np.float32)
-t[np.arange(bunch), rng.randint(0, sizes[-1], bunch)] = 1
+x, t = CFG.synthetic_bunch(name, 1)
 tr.stage(x, t, bunch)
 for _ in range(6):
     tr.step_staged(bunch)
