@@ -172,6 +172,14 @@ int gemm_tc(b200_ctx *ctx, int transA, int transB, int M, int N, int K, const fl
 int gemm_dispatch(b200_ctx *ctx, int transA, int transB, int M, int N, int K, const float *A,
                   int lda, const float *B, int ldb, float *C, int ldc, const GemmEpilogue &ep);
 void gemm_tc_destroy(b200_ctx *ctx);
+// conv_tc.cu: the convolution contractions on the tensor cores (im2col + gemm_tc)
+bool conv_tc_applicable(b200_ctx *ctx, int B, int C, int H, int W, int n, int kh, int kw, int sh, int sw);
+int conv_tc_fwd(b200_ctx *ctx, int B, int C, int H, int W, int n, int kh, int kw, int sh, int sw, const float *x, const float *w,
+                const float *bias, int act, float *y);
+int conv_tc_bwd_data(b200_ctx *ctx, int B, int C, int H, int W, int n, int kh, int kw, int sh, int sw, const float *dy,
+                     const float *w, float *dx);
+int conv_tc_bwd_weight(b200_ctx *ctx, int B, int C, int H, int W, int n, int kh, int kw, int sh, int sw, const float *dy,
+                       const float *x, float scale, float beta, float *dw);
 // skinny.cu: layers with N <= 16 output neurons and the bias gradient (HBM-bound, exact fp32)
 bool skinny_applicable(int M, int N, int K);
 int skinny_fwd(b200_ctx *ctx, int M, int N, int K, const float *X, int ldx, const float *W, int ldw, const float *bias,

@@ -99,19 +99,25 @@ void pick_tile(int M, int N, int K, int sm_count, bool allow_split, bool reduce_
   for (int bn = 256; bn >= 32; bn -= 32) {
     const int tn = (N + bn - 1) / bn;
     const long tiles = (long)tiles_m * tn;
-    for (int split = 1; split <= 2; ++split) {
-      // exchange mode needs both CTAs of a pair resident at once (one wave); reduce-add units are independent
-      if (split == 2 && (!allow_split || num_k < 8 || (!reduce_add && 2 * tiles > sm_count))) continue;
+    // exchange mode: one tile per cluster pair, both CTAs resident at once.  reduce-add mode: the k slices are
+    // independent units of the persistent CTAs, so a problem with few output tiles and a long contraction (the
+    // weight gradient of a convolution: 2 tiles, 1024 k-blocks) is cut into as many slices as it takes to fill
+    // the device.  More than two slices per tile make the fp32 summation order run-dependent (last bits only).
+    const int max_split = reduce_add ? 64 : 2;
+    for (int split = 1; split <= max_split; split *= 2) {
+      if (split >= 2 && (!allow_split || num_k < 4 * split)) continue;
+      if (split == 2 && !reduce_add && 2 * tiles > sm_count) continue;
+      if (split > 2 && tiles * (split / 2) >= sm_count) continue;     // already more units than SMs with fewer slices
       const long ctas = tiles * split;
       const long waves = (ctas + sm_count - 1) / sm_count;
       const double active = (double)(ctas < sm_count ? ctas : sm_count);
       const double kblock = fmax(610.0, active * (16384.0 + 128.0 * bn) / 7300.0);
-      const double kblocks = (split == 2) ? (double)((num_k + 1) / 2) : (double)num_k;
+      const double kblocks = (double)((num_k + split - 1) / split);
       double cost;
       if (reduce_add) {
         // persistent CTAs: the epilogue of a unit runs under the next unit's main loop, only the last one is exposed
         // (every CTA drains a whole 128 x bn tile)
-        cost = (double)waves * kblocks * kblock + (bn / 32) * 350.0 + (waves > 1 ? 600.0 : 0.0);
+        cost = (double)waves * kblocks * kblock + (bn / 32) * 350.0 + (waves > 1 ? 600.0 : 0.0) + 50.0 * split;
       } else {
         cost = (double)waves * kblocks * kblock + (bn / 32) * 500.0 / split;
         if (split == 2) cost += 1500.0 + (bn / 64) * 450.0;   // two cluster barriers + DSMEM exchange of half a tile
@@ -188,6 +194,12 @@ int gemm_tc(b200_ctx *ctx, int transA, int transB, int M, int N, int K, const fl
     p.BN = s->force_bn & 0xfff;
     p.splitk = (s->force_bn & 0x1000) ? 2 : 1;
   }
+  if (p.splitk > 2 && !p.reduce_add) p.splitk = 2;
+  {
+    // no empty k slice: every unit must issue at least one MMA (its accumulator is added as it stands)
+    const int nk = (K + BK - 1) / BK;
+    while (p.splitk > 1 && (p.splitk - 1) * ((nk + p.splitk - 1) / p.splitk) >= nk) p.splitk /= 2;
+  }
   // the ring is as deep as shared memory allows: loads are latency/bandwidth bound, so bytes in flight matter
   p.stage_bytes = (uint32_t)A_BYTES + (b_k ? (uint32_t)p.BN * BK * 4 : (uint32_t)((p.BN + 31) / 32) * 4096u);
   {
@@ -246,7 +258,7 @@ int gemm_tc(b200_ctx *ctx, int transA, int transB, int M, int N, int K, const fl
   }
 
   const int tiles = ((M + BM - 1) / BM) * tiles_n;
-  if (p.splitk == 2 && ((!p.reduce_add && 2 * tiles > sms) || (p.BN & 31) != 0 || (K + BK - 1) / BK < 2)) p.splitk = 1;
+  if (p.splitk >= 2 && ((!p.reduce_add && 2 * tiles > sms) || (p.BN & 31) != 0 || (K + BK - 1) / BK < p.splitk)) p.splitk = 1;
   // the exchange area of a split-K pair (half a tile per CTA) lives in the operand ring
   if (p.splitk == 2 && !p.reduce_add) {
     // receive area (4 quadrants x own chunks) + send staging (8 warps x half of the peer's chunks), 4 KiB each

@@ -298,14 +298,18 @@ def test_c4_conv_net_steps_vs_oracle(ann, mode, tol, bunch):
                 ref.optimizer.update[n][...] = tr.updates(n)
 
 
-@pytest.mark.parametrize("B,C,H,W,n,k", [(512, 1, 28, 28, 16, 5), (512, 16, 12, 12, 32, 5)])
-def test_c4_convolution_shapes_tensor_core(ann, ops, B, C, H, W, n, k):
-    """The two convolutions of C4 at full bunch in TF32 mode (implicit GEMM on tcgen05), every pass
-    against the oracle's per-pixel GEMM restatement."""
+@pytest.mark.parametrize("B,C,H,W,n,kh,kw,sh,sw", [(512, 1, 28, 28, 16, 5, 5, 1, 1), (512, 16, 12, 12, 32, 5, 5, 1, 1),
+                                                   (64, 10, 7, 7, 20, 2, 2, 1, 1), (32, 8, 9, 9, 10, 3, 3, 1, 1),
+                                                   (40, 6, 13, 11, 12, 3, 4, 2, 1), (16, 5, 20, 20, 9, 5, 5, 1, 2)])
+def test_c4_convolution_shapes_tensor_core(ann, ops, B, C, H, W, n, kh, kw, sh, sw):
+    """The convolutions of C4 at full bunch in TF32 mode (window matrix + tcgen05 contraction, csrc/conv_tc.cu; the
+    first one, a 25-value window, stays on the direct kernels), plus shapes that exercise the padding of the
+    tensor path (plane counts and window lengths that are not multiples of 4, strides, ragged pixel tiles):
+    every pass against the oracle's per-pixel GEMM restatement."""
     x = rnd(140, B, C, H, W)
-    w = rnd(141, n, C * k * k, lo=-0.2, hi=0.2)
+    w = rnd(141, n, C * kh * kw, lo=-0.2, hi=0.2)
     bias = rnd(142, n)
-    conv = A.Convolution((C, k, k), n, "w")
+    conv = A.Convolution((C, kh, kw), n, "w", step=(1, sh, sw))
     weights = {}
     conv.build(0, weights)
     weights["w"][...] = w
@@ -315,9 +319,11 @@ def test_c4_convolution_shapes_tensor_core(ann, ops, B, C, H, W, n, k):
     g, c = {}, {}
     conv.compute_gradients(g, c)
     with math_mode(ann, "tf32"):
-        y = ops.conv2d_fwd(x, w, (k, k), (1, 1), bias=bias, act="relu")
-        dx = ops.conv2d_bwd_data(dy, w, x.shape, (k, k), (1, 1))
-        dw, db = ops.conv2d_bwd_weight(dy, x, (k, k), (1, 1), scale=0.125)
+        y = ops.conv2d_fwd(x, w, (kh, kw), (sh, sw), bias=bias, act="relu")
+        y_lin = ops.conv2d_fwd(x, w, (kh, kw), (sh, sw))
+        dx = ops.conv2d_bwd_data(dy, w, x.shape, (kh, kw), (sh, sw))
+        dw, db = ops.conv2d_bwd_weight(dy, x, (kh, kw), (sh, sw), scale=0.125)
+    assert rel_l2(y_lin, y_ref) < TF32_TOL
     assert rel_l2(y, A.relu(y_ref + bias[None, :, None, None])) < TF32_TOL
     assert rel_l2(dx, dx_ref) < TF32_TOL
     assert rel_l2(dw, 0.125 * g["w"]) < TF32_TOL
