@@ -198,6 +198,140 @@ dp_fused_update_kernel(const b200_dp_group grp, const b200_sgd_tensor *__restric
   }
 }
 
+// ---------------------------------------------------------------- NVLS (in-switch) variant
+// With the gradient and weight arenas of every rank bound to one multicast object (NVLink SHARP / NVLS, set up by the
+// host through CUDA's multicast API: cuMulticastCreate / cuMulticastBindMem, done for us by torch's symmetric memory
+// allocator, april_ann_b200/parallel.py), the reduce-scatter and the all-gather become ONE instruction each per
+// 16 bytes:
+//   multimem.ld_reduce.add.v4.f32 [mc_grads + i]   the NVSwitch reads the 16 bytes from every replica, adds them
+//                                                  and returns the sum -- instead of (N-1) P2P loads per element
+//   multimem.st.v4.f32 [mc_weights + i], w         the NVSwitch writes the new weights into every replica
+//                                                  -- instead of (N-1) P2P stores per element
+// so a rank issues 1/N of the loads of the pull kernel above and the switch does the fan-in / fan-out.  Same tags,
+// same shard plan, same SGD arithmetic.  The summation order inside the switch is the hardware's; every element
+// is reduced exactly once (by its owner), so the replicas stay bit-identical.
+__device__ __forceinline__ float4 multimem_ld_reduce_add(const float4 *mc) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(mc)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void multimem_st(float4 *mc, const float4 &v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+template <int DP_UNROLL>
+__global__ void __launch_bounds__(DP_THREADS, 1)
+dp_mc_update_kernel(const b200_dp_group grp, const b200_sgd_tensor *__restrict__ tensors, int ntensors, double decay,
+                    int64_t *count_dev, int bucket) {
+  const int rank = grp.rank, nranks = grp.nranks;
+  const int64_t count = *reinterpret_cast<volatile int64_t *>(count_dev);
+  const long long tag = (long long)*reinterpret_cast<volatile int64_t *>(count_dev + 2) + 1;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *dbg_slot(grp.flags[rank], bucket, 0) = gtime();
+  constexpr int MAXT = 32;
+  __shared__ unsigned long long s_cum[MAXT + 1], s_lo[MAXT], s_off4[MAXT];
+  __shared__ float4 *s_u[MAXT];
+  __shared__ float s_lrd[MAXT], s_mt[MAXT], s_l2[MAXT], s_l1[MAXT];
+  const double dec = 1.0 / (1.0 + decay * (double)count);
+  const bool prune = (count % 100) == 0;
+  const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (unsigned long long)gridDim.x * blockDim.x;
+  if (threadIdx.x == 0) {
+    unsigned long long cum = 0;
+    for (int ti = 0; ti < ntensors; ++ti) {
+      const b200_sgd_tensor t = tensors[ti];
+      const size_t n4 = (t.n + 3) >> 2;
+      const size_t per = (n4 + nranks - 1) / nranks;
+      const size_t lo = min(n4, (size_t)rank * per), hi = min(n4, lo + per);
+      s_cum[ti] = cum;
+      s_lo[ti] = lo;
+      s_off4[ti] = (unsigned long long)(t.w - grp.weights[rank]) >> 2;
+      s_u[ti] = reinterpret_cast<float4 *>(t.u);
+      s_lrd[ti] = (float)((double)t.lr * dec);
+      s_mt[ti] = t.momentum;
+      s_l2[ti] = t.weight_decay;
+      s_l1[ti] = t.l1_norm > 0.0f ? (float)(((double)t.lr * dec) * (double)t.l1_norm) : 0.0f;
+      cum += hi - lo;
+    }
+    s_cum[ntensors] = cum;
+  }
+  // announce (gradients final, weights of the bucket no longer read by this rank's data gradients), wait for every peer
+  if (threadIdx.x < nranks) st_release_sys(ready_slot(grp.flags[threadIdx.x], bucket, rank), tag);
+  if (threadIdx.x < nranks) {
+    const long long *f = ready_slot(grp.flags[rank], bucket, threadIdx.x);
+    while (ld_acquire_sys(f) < tag) { }
+  }
+  __syncthreads();
+  if (blockIdx.x == 0 && threadIdx.x == 0) *dbg_slot(grp.flags[rank], bucket, 1) = gtime();
+  auto locate = [&](unsigned long long gc, int &ti) {
+    ti = 0;
+    while (ti + 1 < ntensors && gc >= s_cum[ti + 1]) ++ti;
+    return s_off4[ti] + s_lo[ti] + (gc - s_cum[ti]);
+  };
+  const float4 *mc_g = reinterpret_cast<const float4 *>(grp.mc_grads);
+  float4 *mc_w = reinterpret_cast<float4 *>(grp.mc_weights);
+  const float4 *own_w = reinterpret_cast<const float4 *>(grp.weights[rank]);
+  const unsigned long long total = s_cum[ntensors];
+  for (unsigned long long i = tid; i < total; i += DP_UNROLL * nth) {
+    float4 g[DP_UNROLL], w[DP_UNROLL], u[DP_UNROLL];
+    int tix[DP_UNROLL];
+    unsigned long long el[DP_UNROLL];
+    bool ok[DP_UNROLL];
+#pragma unroll
+    for (int j = 0; j < DP_UNROLL; ++j) {
+      const unsigned long long gi = i + (unsigned long long)j * nth;
+      ok[j] = gi < total;
+      el[j] = locate(ok[j] ? gi : 0ull, tix[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < DP_UNROLL; ++j) {   // 3 x DP_UNROLL independent 16-byte loads in flight
+      g[j] = multimem_ld_reduce_add(mc_g + el[j]);
+      w[j] = own_w[el[j]];
+      u[j] = __ldcs(s_u[tix[j]] + (el[j] - s_off4[tix[j]]));
+    }
+#pragma unroll
+    for (int j = 0; j < DP_UNROLL; ++j) {
+      if (!ok[j]) continue;
+      const float lrd = s_lrd[tix[j]], mt = s_mt[tix[j]], l2 = s_l2[tix[j]], l1 = s_l1[tix[j]];
+      auto upd = [&](float &wv, float &gv, float &uv) {   // optimizer_sgd.lua:65-95, same order as sgd.cu
+        if (l2 > 0.0f) gv = fmaf(l2, wv, gv);
+        uv = (mt > 0.0f) ? mt * uv : 0.0f;
+        uv = fmaf(lrd, gv, uv);
+        wv -= uv;
+        if (l1 > 0.0f) {
+          const float z = fabsf(wv) > l1 ? 1.0f : 0.0f;
+          const float sg = (wv > 0.0f) ? l1 : (wv < 0.0f ? -l1 : 0.0f);
+          wv -= sg;
+          uv -= sg;
+          wv *= z;
+        }
+        if (prune && fabsf(wv) < FLT_MIN) wv = 0.0f;
+      };
+      upd(w[j].x, g[j].x, u[j].x); upd(w[j].y, g[j].y, u[j].y); upd(w[j].z, g[j].z, u[j].z); upd(w[j].w, g[j].w, u[j].w);
+      __stcs(s_u[tix[j]] + (el[j] - s_off4[tix[j]]), u[j]);
+      multimem_st(mc_w + el[j], w[j]);      // into every replica, this rank's own included
+    }
+  }
+  __shared__ int s_last;
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long *ticket = ticket_slot(grp.flags[rank], 1);
+    s_last = atomicAdd(ticket, 1ull) == (unsigned long long)gridDim.x - 1;
+    if (s_last) {
+      *ticket = 0ull;
+      *dbg_slot(grp.flags[rank], bucket, 2) = gtime();
+    }
+  }
+  __syncthreads();
+  if (s_last) {
+    if (threadIdx.x < nranks) st_release_sys(done_slot(grp.flags[threadIdx.x], bucket, rank), tag);
+    if (threadIdx.x == 0) *dbg_slot(grp.flags[rank], bucket, 3) = gtime();
+  }
+}
+
 // ---------------------------------------------------------------- copy-engine variant
 // The same protocol with the NVLink traffic on the copy engines instead of SM loads / stores: the update
 // kernel shrinks to a local pass (16 us for the 17 MB bucket on 74 SMs) and the SMs stay free, but every
@@ -423,6 +557,18 @@ extern "C" int b200_dp_fused_update(b200_ctx *ctx, const b200_dp_group *grp, int
   }
   size_t shard4 = 0;   // float4 of this rank's shards: enough CTAs to cover them once, at most the SMs planned for
   for (int i = 0; i < ntensors; ++i) shard4 += (((size_t)tensors_host[i].n + 3) / 4 + grp->nranks - 1) / grp->nranks;
+  if (grp->mc_grads && grp->mc_weights) {
+    // the arenas are bound to a multicast object: the NVSwitch reduces and broadcasts (dp_mc_update_kernel)
+    constexpr int UN = 4;
+    auto kern = dp_mc_update_kernel<UN>;
+    if (ONCE_PER_DEVICE(ctx)) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DP_SMEM));
+    size_t blocks = (shard4 + (size_t)DP_THREADS * UN - 1) / ((size_t)DP_THREADS * UN);
+    if (blocks > (size_t)sms) blocks = (size_t)sms;
+    if (blocks < 1) blocks = 1;
+    kern<<<(unsigned)blocks, DP_THREADS, DP_SMEM, ctx->stream>>>(*grp, tensors_dev, ntensors, decay, count_dev, bucket);
+    LAUNCH_CHECK(ctx);
+    return B200_OK;
+  }
 #define DP_LAUNCH(NR, UN)                                                                                         \
   do {                                                                                                            \
     auto kern = dp_fused_update_kernel<NR, UN>;                                                                   \

@@ -419,10 +419,18 @@ class SupervisedTrainer {
   // this rank's weight arena, gradient arena and flag block (3 x 64 bytes); dpConnect maps every peer's
   void dpExport(int nranks, unsigned char *handles256);
   void dpConnect(int nranks, int rank, const unsigned char *all_handles);
+  // replica group over SYMMETRIC memory: every rank's [weights | gradients | flags] live at the same offsets of a
+  // buffer that is mapped into every process (bases[r]) and bound to a multicast object (mc_base, may be NULL).
+  // The trainer moves its weight and gradient arenas into its own buffer (bases[rank]).
+  void dpConnectSymmetric(int nranks, int rank, void *const *bases, void *mc_base, size_t bytes);
+  static size_t dpSymmetricBytes(size_t arena_floats);
+  void rehomeArenas(float *w, float *g);
+  unsigned build_in = 0, build_out = 0;
   float dpBench(int reps);
   bool dp_fused = false;
   b200_dp_group dp_group = {};
   long long *dp_flags = nullptr;
+  bool dp_flags_owned = true;            // false: the flag block lives in the caller's symmetric buffer
   float *dp_recv = nullptr;
   std::vector<void *> dp_imported;
 

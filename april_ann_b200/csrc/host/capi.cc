@@ -322,6 +322,17 @@ int b200h_trainer_dp_debug(b200_trainer *t, long long *stamps64) {
 int b200h_trainer_dp_export(b200_trainer *t, int nranks, void *handles256) {
   API_TRY(t->t->dpExport(nranks, (unsigned char *)handles256))
 }
+size_t b200h_trainer_dp_symmetric_bytes(b200_trainer *t) {
+  try {
+    if (!t->t->weights_arena) return 0;
+    return SupervisedTrainer::dpSymmetricBytes(t->t->weights_arena->size());
+  } catch (...) {
+    return 0;
+  }
+}
+int b200h_trainer_dp_connect_symmetric(b200_trainer *t, int nranks, int rank, void *const *bases, void *mc_base, size_t bytes) {
+  API_TRY(t->t->dpConnectSymmetric(nranks, rank, bases, mc_base, bytes))
+}
 int b200h_trainer_dp_connect(b200_trainer *t, int nranks, int rank, const void *all_handles) {
   API_TRY(t->t->dpConnect(nranks, rank, (const unsigned char *)all_handles))
 }

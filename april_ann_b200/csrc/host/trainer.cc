@@ -193,11 +193,13 @@ SupervisedTrainer::~SupervisedTrainer() {
   if (opt_dev) b200_free(ctx, opt_dev);
   if (norm_dev) b200_free(ctx, norm_dev);
   for (void *p : dp_imported) b200_ipc_close(ctx, p);
-  if (dp_flags) b200_free(ctx, dp_flags);
+  if (dp_flags && dp_flags_owned) b200_free(ctx, dp_flags);
   if (dp_recv) b200_free(ctx, dp_recv);
 }
 
 void SupervisedTrainer::build(unsigned input, unsigned output) {
+  build_in = input;
+  build_out = output;
   net->setContext(ctx);
   // pass 1: discover weight names and shapes
   MatrixDict discovered;
@@ -638,6 +640,10 @@ void SupervisedTrainer::runStep(const MatrixPtr &x, const MatrixPtr &t, int glob
     int nextb = 0, nbuckets = 0;
     auto launchBucket = [&](int lo, int hi, bool last) {
       if (last) {
+        // The last bucket waits for EVERY branch, the earlier buckets on branch 0 included.  (Letting it run beside
+        // them was tried at N = 8 and deadlocked the replica group: the kernels spin on cross-GPU tags and rely on
+        // every CTA of a launch being resident; two such launches plus a contraction on one device break that
+        // guarantee, and a rank whose CTAs cannot all start stalls every peer.)
         check(b200_branch_join_all(ctx));
       } else if (use_branches) {
         check(b200_branch_begin(ctx, 0));
@@ -1098,6 +1104,70 @@ void SupervisedTrainer::dpConnect(int nranks, int rank, const unsigned char *all
     dp_group.flags[p] = (long long *)ptr[2];
     dp_group.recv[p] = (float *)ptr[3];
   }
+  dp_fused = true;
+  if (const char *e = getenv("B200_DP_FUSED")) dp_fused = atoi(e) != 0;
+  invalidateGraphs();
+}
+
+// Moves the weight and gradient arenas into caller-provided device memory (same layout), e.g. a buffer that is
+// mapped into every process of a replica group.  Every view and every component is re-bound.
+void SupervisedTrainer::rehomeArenas(float *w, float *g) {
+  if (weights_order.empty()) throw Error(B200_ERR_NOT_BUILT, "Execute build method before joining a replica group");
+  check(b200_sync(ctx));
+  invalidateGraphs();
+  const int total = (int)weights_arena->size();
+  MatrixPtr nw = Matrix::wrap(ctx, w, std::vector<int>{total}), ng = Matrix::wrap(ctx, g, std::vector<int>{total});
+  nw->copyFrom(*weights_arena);
+  ng->copyFrom(*grads_arena);
+  check(b200_sync(ctx));
+  std::map<std::string, size_t> offs;
+  for (auto &n : weights_order) offs[n] = (size_t)(weights_table[n]->data - weights_arena->data);
+  weights_arena = nw;
+  grads_arena = ng;
+  for (auto &n : weights_order) {
+    const std::vector<int> d = weights_table[n]->dims;
+    weights_table[n] = Matrix::view(weights_arena, offs[n], d);
+    grads[n] = Matrix::view(grads_arena, offs[n], d);
+  }
+  ComponentDict comps;
+  net->build(build_in, build_out, weights_table, comps);
+  sgd_dirty = true;
+}
+
+size_t SupervisedTrainer::dpSymmetricBytes(size_t arena_floats) {
+  const size_t a = (arena_floats * sizeof(float) + 1023) & ~size_t(1023);
+  return 2 * a + ((b200_dp_flags_bytes() + 1023) & ~size_t(1023));
+}
+
+void SupervisedTrainer::dpConnectSymmetric(int nranks, int rank, void *const *bases, void *mc_base, size_t bytes) {
+  if (nranks < 2 || nranks > B200_DP_MAX_RANKS) throw Error(B200_ERR_BAD_ARG, "replica group of 2..8 ranks");
+  const size_t floats = weights_arena->size();
+  const size_t a = (floats * sizeof(float) + 1023) & ~size_t(1023);
+  if (bytes < dpSymmetricBytes(floats)) throw Error(B200_ERR_BAD_ARG, "symmetric buffer too small (b200h_trainer_dp_symmetric_bytes)");
+  for (int p = 0; p < nranks; ++p)
+    if (!bases[p]) throw Error(B200_ERR_BAD_ARG, "dpConnectSymmetric: NULL base pointer");
+  char *mine = (char *)bases[rank];
+  rehomeArenas((float *)mine, (float *)(mine + a));
+  check(b200_memset_zero(ctx, mine + 2 * a, b200_dp_flags_bytes()));
+  check(b200_sync(ctx));
+  if (dp_flags && dp_flags_owned) b200_free(ctx, dp_flags);
+  dp_flags = (long long *)(mine + 2 * a);
+  dp_flags_owned = false;
+  dp_group = b200_dp_group{};
+  dp_group.nranks = nranks;
+  dp_group.rank = rank;
+  dp_group.arena_elems = floats;
+  for (int p = 0; p < nranks; ++p) {
+    char *b = (char *)bases[p];
+    dp_group.weights[p] = (float *)b;
+    dp_group.grads[p] = (float *)(b + a);
+    dp_group.flags[p] = (long long *)(b + 2 * a);
+    dp_group.recv[p] = nullptr;    // (no receive blocks: the copy-engine / push variants are not available here)
+  }
+  dp_group.mc_weights = mc_base ? (float *)mc_base : nullptr;
+  dp_group.mc_grads = mc_base ? (float *)((char *)mc_base + a) : nullptr;
+  if (const char *e = getenv("B200_DP_MULTICAST"))
+    if (atoi(e) == 0) dp_group.mc_weights = dp_group.mc_grads = nullptr;   // same memory, P2P pull kernel
   dp_fused = true;
   if (const char *e = getenv("B200_DP_FUSED")) dp_fused = atoi(e) != 0;
   invalidateGraphs();

@@ -48,9 +48,13 @@ def exchange_unique_id(dist):
     return obj[0]
 
 
-def init_data_parallel(trainer, dist, fused=True):
+def init_data_parallel(trainer, dist, fused=True, multicast=True):
     """Creates the NCCL communicator of the trainer's context, makes the trainer scale gradients
-    by the global bunch and all-reduce them, and broadcasts rank 0's weights to every replica."""
+    by the global bunch and all-reduce them, and broadcasts rank 0's weights to every replica.
+    fused: the update of a step runs as one kernel per bucket over NVLink peer memory -- through the NVSwitch's
+    in-switch reduction (multicast / NVLS) when `multicast` and the fabric allow it, else with P2P loads and
+    stores (CUDA IPC mappings)."""
+    import os
     world, rank = dist.get_world_size(), dist.get_rank()
     uid = exchange_unique_id(dist)
     check(lib.b200_comm_init(trainer.ctx.h, C.c_int(world), C.c_int(rank), uid))
@@ -58,8 +62,79 @@ def init_data_parallel(trainer, dist, fused=True):
     trainer.broadcast_weights()
     dist.barrier()
     if fused and 2 <= world <= 8:
-        connect_peer_memory(trainer, dist)
+        done = False
+        # Transport of the fused update (measured on the pool's boxes, C2, profiles/dp_r2.md):
+        #   2 GPUs: P2P loads / stores 175 us per step, in-switch reduction (NVLS multicast) 217 us
+        #   8 GPUs: P2P 205 us, NVLS 201 us
+        # so the multicast path is the default from 8 ranks on; B200_DP_SYMMETRIC=1 / 0 forces it on / off.
+        want = os.environ.get("B200_DP_SYMMETRIC")
+        use_symm = multicast and (world >= 8 if want is None else want != "0")
+        if use_symm:
+            done = connect_symmetric_memory(trainer, dist)
+        if not done:
+            connect_peer_memory(trainer, dist)
     dist.barrier()
+
+
+def connect_symmetric_memory(trainer, dist):
+    """Allocates this rank's [weights | gradients | flags] block in symmetric memory (torch's allocator: CUDA VMM
+    allocations exchanged between the processes and bound to a multicast object -- plumbing only), hands the
+    mapped addresses to the trainer.  Every rank must succeed, otherwise all of them use the IPC path."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    ok, keep, mc = True, None, 0
+    # the rendezvous below is a collective: agree first that every rank can take part at all (imports, a device
+    # that supports multicast objects), so that no rank waits inside it for one that never arrives
+    try:
+        import torch
+        import torch.distributed._symmetric_memory as symm_mem
+        from cuda import cuda as _cu
+        _cu.cuInit(0)
+        _, _dev = _cu.cuDeviceGet(trainer.ctx.device)
+        _, _mcs = _cu.cuDeviceGetAttribute(_cu.CUdevice_attribute.CU_DEVICE_ATTRIBUTE_MULTICAST_SUPPORTED, _dev)
+        pre = bool(_mcs) and torch.cuda.is_available()
+    except Exception:
+        pre = False
+    agree = [None] * world
+    dist.all_gather_object(agree, pre)
+    if not all(agree):
+        return False
+    try:
+        lib.b200h_trainer_dp_symmetric_bytes.restype = C.c_size_t
+        nbytes = int(lib.b200h_trainer_dp_symmetric_bytes(trainer.h))
+        if nbytes <= 0:
+            raise RuntimeError("trainer not built")
+        dev = torch.device("cuda", trainer.ctx.device)
+        torch.cuda.set_device(dev)
+        buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=dev)
+        hdl = symm_mem.rendezvous(buf, dist.group.WORLD.group_name)
+        bases = [int(p) for p in hdl.buffer_ptrs]
+        mc = int(hdl.multicast_ptr) if getattr(hdl, "multicast_ptr", 0) else 0
+        keep = (buf, hdl)
+        if len(bases) != world or not all(bases):
+            raise RuntimeError("incomplete peer mapping")
+    except Exception:
+        ok = False
+    flags = [None] * world
+    dist.all_gather_object(flags, (ok, bool(ok and mc)))
+    if not all(f[0] for f in flags):
+        return False
+    if not all(f[1] for f in flags):
+        mc = 0     # some rank has no multicast mapping: everybody uses P2P loads / stores on the symmetric buffers
+    torch.cuda.synchronize()
+    arr = (C.c_void_p * world)(*bases)
+    try:
+        check(lib.b200h_trainer_dp_connect_symmetric(trainer.h, C.c_int(world), C.c_int(rank), arr, C.c_void_p(mc or None),
+                                                     C.c_size_t(nbytes)))
+    except Exception:
+        ok = False
+    dist.all_gather_object(flags, ok)
+    if not all(flags):
+        if ok:
+            trainer.set_flag("dp_fused", 0)
+        return False
+    trainer._symmetric = keep       # the allocation lives as long as the trainer
+    trainer.dp_transport = "multicast" if mc else "symmetric-p2p"
+    return True
 
 
 def connect_peer_memory(trainer, dist):

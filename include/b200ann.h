@@ -283,6 +283,10 @@ typedef struct {
   long long *flags[B200_DP_MAX_RANKS];  /* every rank's flag block */
   uint64_t arena_elems;                 /* floats of one arena (same on every rank) */
   int32_t nranks, rank;
+  /* NVLS: multicast addresses of the gradient / weight arenas when every rank's arenas are bound to one multicast
+   * object (NULL otherwise).  multimem.ld_reduce on mc_grads sums the replicas inside the NVSwitch, multimem.st on
+   * mc_weights writes every replica. */
+  float *mc_grads, *mc_weights;
 } b200_dp_group;
 int b200_ipc_export(b200_ctx *ctx, void *dptr, void *handle64);
 int b200_ipc_import(b200_ctx *ctx, const void *handle64, void **dptr);

@@ -140,6 +140,13 @@ int b200h_trainer_dp_export(b200_trainer *t, int nranks, void *handles256);
 int b200h_trainer_dp_bench(b200_trainer *t, int reps, float *us_per_update);
 int b200h_trainer_dp_debug(b200_trainer *t, long long *stamps64);   /* 4 globaltimer stamps per bucket of the last step */
 int b200h_trainer_dp_connect(b200_trainer *t, int nranks, int rank, const void *all_handles);
+/* replica group over symmetric memory (NVLS): every rank allocates b200h_trainer_dp_symmetric_bytes() bytes that
+ * are mapped into every process (bases[r] = rank r's buffer as THIS process addresses it) and, where the fabric
+ * supports it, bound to one multicast object (mc_base; NULL: P2P loads / stores on the same buffers).  The trainer
+ * moves its weight and gradient arenas into its own buffer; afterwards the update of a step is one kernel per
+ * bucket in which the NVSwitch sums the gradients (multimem.ld_reduce) and broadcasts the new weights (multimem.st). */
+size_t b200h_trainer_dp_symmetric_bytes(b200_trainer *t);
+int b200h_trainer_dp_connect_symmetric(b200_trainer *t, int nranks, int rank, void *const *bases, void *mc_base, size_t bytes);
 
 #ifdef __cplusplus
 }
