@@ -621,7 +621,8 @@ class CrossEntropy(Loss):
     def loss_rows(self, o, t):
         le, l1e = np.log(NEAR_ZERO).astype(f32), np.log(f32(1.0) - NEAR_ZERO).astype(f32)
         log_o = np.clip(o, le, l1e).astype(f32)
-        od = np.exp(log_o.astype(np.float64))
+        # `double o = m_exp(log_o)`: the exponential is the float one, only the log(1-o) is double
+        od = np.exp(log_o, dtype=f32).astype(np.float64)
         log_inv_o = np.log(1.0 - od).astype(f32)
         tc = np.clip(t, NEAR_ZERO, f32(1.0) - NEAR_ZERO).astype(f32)
         inv_t = np.clip((f32(1.0) - t).astype(f32), NEAR_ZERO, f32(1.0) - NEAR_ZERO).astype(f32)
