@@ -16,7 +16,9 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "_ref", "libaprilref.so")
+# APRILREF_LIB selects another build of the same C face: the integration builds
+# (integration/_build/libaprilref_{shim,b200}.so) are driven through this module too.
+LIB_PATH = os.environ.get("APRILREF_LIB") or os.path.join(HERE, "_ref", "libaprilref.so")
 
 _lib = None
 _F = C.POINTER(C.c_float)
@@ -52,6 +54,8 @@ def lib():
         L.ref_rewrap_new.argtypes = [_I, C.c_int]
         L.ref_dropout_new.argtypes = [C.c_uint, C.c_float, C.c_float, C.c_int]
         L.ref_component_free.argtypes = [C.c_void_p]
+        L.ref_component_set_use_cuda.argtypes = [C.c_void_p, C.c_int]
+        L.ref_set_use_cuda_default.argtypes = [C.c_int]
         L.ref_net_build.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.ref_net_free.argtypes = [C.c_void_p]
         L.ref_net_tensor_get.argtypes = [C.c_void_p, C.c_int, C.c_char_p, _F, C.c_int, _I, _I]
@@ -105,6 +109,21 @@ def _b(s):
 
 
 # ---- component constructors (ann.components.*) ---------------------------
+
+def built_with_cuda():
+    return bool(lib().ref_built_with_cuda())
+
+
+def set_use_cuda_default(flag):
+    """mathcore.set_use_cuda_default(flag)."""
+    lib().ref_set_use_cuda_default(int(flag))
+
+
+def set_use_cuda(component, flag):
+    """component:set_use_cuda(flag); call before Net(...) builds it."""
+    lib().ref_component_set_use_cuda(component, int(flag))
+    return component
+
 
 def stack():
     return lib().ref_stack_new()

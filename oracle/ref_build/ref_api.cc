@@ -138,6 +138,24 @@ int ref_init(void) {
   return 0;
 }
 
+// 1 when this library is the reference's USE_CUDA build (integration/Makefile).
+int ref_built_with_cuda(void) {
+#ifdef USE_CUDA
+  return 1;
+#else
+  return 0;
+#endif
+}
+// mathcore.set_use_cuda_default (mathcore/binding/bind_mathcore.lua.cc:157-163):
+// matrices and components created from now on compute on the device.
+void ref_set_use_cuda_default(int flag) {
+  AprilMath::GPUMirroredMemoryBlockBase::USE_CUDA_DEFAULT = (flag != 0);
+}
+// component:set_use_cuda(flag) (ann_component.h:378-388); recursive for a stack.
+void ref_component_set_use_cuda(void* comp, int flag) {
+  static_cast<ANNComponent*>(comp)->setUseCuda(flag != 0);
+}
+
 // ---- components --------------------------------------------------------
 // Each constructor returns a new ANNComponent* with one reference held by the
 // caller; ref_stack_push hands a second one to the stack.
