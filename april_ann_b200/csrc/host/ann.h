@@ -26,6 +26,8 @@ struct Error : std::runtime_error {
   Error(int c, const std::string &m) : std::runtime_error(m), code(c) {}
 };
 void check(int status);  // throws Error(status, b200_last_error_string())
+// bucket plan of the fused replica-group update (trainer.cc); pure host logic
+bool dp_bucket_plan(const std::vector<size_t> &tensor_bytes, size_t bucket_bytes, std::vector<std::pair<int, int>> *out);
 
 // ---------------------------------------------------------------- MTRand
 class MTRand {
@@ -461,7 +463,7 @@ class SupervisedTrainer {
  private:
   void runStep(const MatrixPtr &x, const MatrixPtr &t, int global_bunch, double max_gradients_norm);
   void runUpdateSimple(double max_gradients_norm);
-  bool dpBucketPlan(std::vector<std::pair<int, int>> *out);
+  bool dpBucketPlan(std::vector<std::pair<int, int>> *out);   // dp_bucket_plan over this trainer's gradients
   b200_opt_tensor *opt_dev = nullptr;
   std::vector<b200_opt_tensor> opt_host;
   float *norm_dev = nullptr;

@@ -322,6 +322,16 @@ int b200h_trainer_dp_debug(b200_trainer *t, long long *stamps64) {
 int b200h_trainer_dp_export(b200_trainer *t, int nranks, void *handles256) {
   API_TRY(t->t->dpExport(nranks, (unsigned char *)handles256))
 }
+int b200h_dp_bucket_plan(const size_t *tensor_bytes, int ntensors, size_t bucket_bytes, int *lo, int *hi, int cap) {
+  if (ntensors < 0 || (ntensors > 0 && !tensor_bytes)) return -1;
+  std::vector<std::pair<int, int>> plan;
+  if (!dp_bucket_plan(std::vector<size_t>(tensor_bytes, tensor_bytes + ntensors), bucket_bytes, &plan)) return -1;
+  for (int i = 0; i < (int)plan.size() && i < cap; ++i) {
+    if (lo) lo[i] = plan[i].first;
+    if (hi) hi[i] = plan[i].second;
+  }
+  return (int)plan.size();
+}
 size_t b200h_trainer_dp_symmetric_bytes(b200_trainer *t) {
   try {
     if (!t->t->weights_arena) return 0;

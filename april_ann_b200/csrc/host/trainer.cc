@@ -474,15 +474,18 @@ MatrixPtr SupervisedTrainer::outputLayerFused(const MatrixPtr &h, const MatrixPt
 // finishes gradients).  b200_dp_fused_update takes at most 32 tensors per launch and the tag block has 16
 // bucket slots; when a net of very many small tensors cannot be cut that way the caller stays on the
 // NCCL all-reduce path, which has no such limits.
-bool SupervisedTrainer::dpBucketPlan(std::vector<std::pair<int, int>> *out) {
-  const int nt = (int)arena_order.size();
-  size_t threshold = dp_bucket_bytes ? dp_bucket_bytes : 1;
+// Buckets of the fused replica-group update over tensors in arena order: each closes once it holds `bucket_bytes`
+// of gradients or 32 tensors (the kernel's shared tables); the threshold doubles until at most 16 buckets remain
+// (the tag block).  False when no such plan exists (more than 16 * 32 tensors): the caller uses the NCCL path.
+bool dp_bucket_plan(const std::vector<size_t> &tensor_bytes, size_t bucket_bytes, std::vector<std::pair<int, int>> *out) {
+  const int nt = (int)tensor_bytes.size();
+  size_t threshold = bucket_bytes ? bucket_bytes : 1;
   for (int attempt = 0; attempt < 32; ++attempt, threshold *= 2) {
     std::vector<std::pair<int, int>> plan;
     int lo = 0;
     size_t bytes = 0;
     for (int i = 0; i < nt; ++i) {
-      bytes += grads[arena_order[i]]->size() * sizeof(float);
+      bytes += tensor_bytes[i];
       if (bytes >= threshold || i + 1 - lo == 32 || i == nt - 1) {
         plan.emplace_back(lo, i + 1);
         lo = i + 1;
@@ -496,6 +499,12 @@ bool SupervisedTrainer::dpBucketPlan(std::vector<std::pair<int, int>> *out) {
     if (nt > 16 * 32) break;
   }
   return false;
+}
+
+bool SupervisedTrainer::dpBucketPlan(std::vector<std::pair<int, int>> *out) {
+  std::vector<size_t> bytes;
+  for (auto &n : arena_order) bytes.push_back(grads[n]->size() * sizeof(float));
+  return dp_bucket_plan(bytes, dp_bucket_bytes, out);
 }
 
 // The update of a step as ONE launch over every tensor once every gradient exists: the path of the

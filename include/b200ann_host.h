@@ -140,6 +140,11 @@ int b200h_trainer_dp_export(b200_trainer *t, int nranks, void *handles256);
 int b200h_trainer_dp_bench(b200_trainer *t, int reps, float *us_per_update);
 int b200h_trainer_dp_debug(b200_trainer *t, long long *stamps64);   /* 4 globaltimer stamps per bucket of the last step */
 int b200h_trainer_dp_connect(b200_trainer *t, int nranks, int rank, const void *all_handles);
+/* The bucket plan the fused update uses, as pure host logic (no device needed): tensors in arena order with
+ * their gradient bytes; buckets [lo[i], hi[i]) of >= bucket_bytes or 32 tensors, at most 16 of them (the
+ * threshold doubles until they fit).  Returns the number of buckets, or -1 when no plan exists (more than
+ * 512 tensors: the trainer then takes the NCCL all-reduce path). */
+int b200h_dp_bucket_plan(const size_t *tensor_bytes, int ntensors, size_t bucket_bytes, int *lo, int *hi, int cap);
 /* replica group over symmetric memory (NVLS): every rank allocates b200h_trainer_dp_symmetric_bytes() bytes that
  * are mapped into every process (bases[r] = rank r's buffer as THIS process addresses it) and, where the fabric
  * supports it, bound to one multicast object (mc_base; NULL: P2P loads / stores on the same buffers).  The trainer

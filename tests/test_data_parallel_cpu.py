@@ -184,3 +184,56 @@ def test_two_rank_gloo_step_equals_single_process_step(tmp_path):
         assert np.array_equal(w0[name], w1[name]), name            # replicas stay identical
         err = np.abs(w0[name] - ref.weights[name]).max()
         assert err < 2e-6, (name, err)                              # == one step on the global bunch
+
+
+# ---- bucket plan of the fused update (pure host logic behind b200h_dp_bucket_plan) ----------------------------
+
+def _bucket_plan(sizes, bucket_bytes):
+    import ctypes as C
+    lib = C.CDLL(os.path.join(ROOT, "april_ann_b200", "libb200ann.so"))
+    lib.b200h_dp_bucket_plan.argtypes = [C.POINTER(C.c_size_t), C.c_int, C.c_size_t, C.POINTER(C.c_int),
+                                         C.POINTER(C.c_int), C.c_int]
+    a = (C.c_size_t * max(len(sizes), 1))(*sizes)
+    lo, hi = (C.c_int * 64)(), (C.c_int * 64)()
+    n = lib.b200h_dp_bucket_plan(a, len(sizes), bucket_bytes, lo, hi, 64)
+    return n, [(lo[i], hi[i]) for i in range(max(n, 0))]
+
+
+def _check_plan(sizes, plan):
+    # contiguous cover of [0, n), at most 32 tensors per bucket (the kernel's shared tables), at most 16 buckets
+    assert plan[0][0] == 0 and plan[-1][1] == len(sizes)
+    assert all(a[1] == b[0] for a, b in zip(plan, plan[1:]))
+    assert all(0 < hi - lo <= 32 for lo, hi in plan)
+    assert len(plan) <= 16
+
+
+def test_bucket_plan_c2_two_large_tensors():
+    mb = 1 << 20
+    sizes = [8192, 2048 * 10 * 4, 8192, 2048 * 2048 * 4, 8192, 784 * 2048 * 4]
+    n, plan = _bucket_plan(sizes, 4 * mb)
+    _check_plan(sizes, plan)
+    assert n == len(plan) == 2          # each closes on its large matrix
+    assert all(sum(sizes[lo:hi]) >= 4 * mb for lo, hi in plan)
+
+
+def test_bucket_plan_deep_net_of_small_layers_is_cut_at_32_tensors():
+    # 20 layers of 128x128 (+ biases): 40 tensors, 1.3 MB -- one 4 MB bucket would exceed the kernel's 32-tensor
+    # tables (this used to fail every step with B200_ERR_BAD_ARG once peer memory was connected)
+    sizes = [128 * 128 * 4, 512] * 20
+    n, plan = _bucket_plan(sizes, 4 << 20)
+    _check_plan(sizes, plan)
+    assert n == 2 and plan[0] == (0, 32)
+
+
+def test_bucket_plan_threshold_doubles_until_sixteen_buckets_suffice():
+    sizes = [1 << 20] * 100            # 100 tensors of 1 MB with a 1 MB threshold would be 100 buckets
+    n, plan = _bucket_plan(sizes, 1 << 20)
+    _check_plan(sizes, plan)
+    assert 7 <= n <= 16
+
+
+def test_bucket_plan_gives_up_beyond_512_tensors():
+    assert _bucket_plan([64] * 600, 1)[0] == -1          # the trainer then takes the NCCL all-reduce path
+    n, plan = _bucket_plan([64] * 512, 1)
+    _check_plan([64] * 512, plan)
+    assert n == 16
