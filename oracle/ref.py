@@ -143,6 +143,15 @@ def dot_product(input, output, weights, transpose=False):
     return lib().ref_dot_product_new(input, output, _b(weights), int(transpose))
 
 
+def b200_dot_product(input, output, weights, transpose=False):
+    """integration builds only: the dot-product component whose dense methods call libb200ann.so
+    (integration/ann/b200_dot_product_component.h)."""
+    fn = lib().ref_b200_dot_product_new
+    fn.restype = C.c_void_p
+    fn.argtypes = [C.c_int, C.c_int, C.c_char_p, C.c_int]
+    return fn(input, output, _b(weights), int(transpose))
+
+
 def bias(size, weights):
     return lib().ref_bias_new(size, _b(weights))
 

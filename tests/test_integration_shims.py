@@ -46,6 +46,22 @@ def test_shims_are_drop_in_on_the_host_branch():
     assert " passed" in r.stdout and "skipped" not in r.stdout.splitlines()[-1], r.stdout[-500:]
 
 
+@pytest.mark.skipif(not (os.path.exists(SHIM) or HAVE_REF), reason="shim build absent and /root/reference absent")
+def test_driver_script_and_component_seam_class_on_the_host_build():
+    """tools/ref_on_b200.py is what the GPU leg runs; on the CPU build set_use_cuda(true) is refused by the
+    reference (it stays on the host), so this exercises the script's plumbing and the B200DotProductANNComponent
+    class (integration/ann/) on its fall-through to the reference's methods."""
+    if not os.path.exists(SHIM):
+        _make(SHIM)
+    env = dict(os.environ, APRILREF_LIB=SHIM, REF_ON_B200_DRY_RUN="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ref_on_b200.py")], env=env, cwd=ROOT,
+                       capture_output=True, text=True, timeout=300)
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert r.returncode == 0 and line, r.stdout[-800:] + r.stderr[-800:]
+    res = json.loads(line[-1])
+    assert res["ok"] and "mlp_component_seam_bunch32" in res["max_rel_err"], res
+
+
 @pytest.mark.skipif(not os.path.exists(GPU), reason="USE_CUDA build of the reference not present (make -C integration)")
 def test_gpu_build_links_the_reference_to_the_c_abi():
     dyn = subprocess.run(["nm", "-D", GPU], capture_output=True, text=True, check=True).stdout
@@ -53,11 +69,14 @@ def test_gpu_build_links_the_reference_to_the_c_abi():
     exported = {ln.split()[-1] for ln in dyn.splitlines() if " T " in ln}
     # what the shims route to the library (integration/mathcore/{gemm,gemv,axpy}_b200.cc, b200_bridge.cc)
     for sym in ("b200_create", "b200_stream", "b200_sgemm", "b200_sgemv", "b200_sger", "b200_saxpy",
-                "b200_bias_fwd", "b200_bias_grad", "b200_last_error_string"):
+                "b200_bias_fwd", "b200_bias_grad", "b200_last_error_string",
+                # integration/ann/b200_dot_product_component.cc
+                "b200_linear_fwd", "b200_linear_bwd_data", "b200_linear_bwd_weight"):
         assert sym in imported, sym
     # the reference's own device code is still there (its map / reduce kernels, cuBLAS level 1)
     assert any(s.startswith("cublas") for s in imported)
-    for sym in ("ref_net_forward", "ref_net_backprop", "ref_component_set_use_cuda", "ref_built_with_cuda"):
+    for sym in ("ref_net_forward", "ref_net_backprop", "ref_component_set_use_cuda", "ref_built_with_cuda",
+                "ref_b200_dot_product_new"):
         assert sym in exported, sym
     # the three replaced translation units are really the shims: doGemm<float> comes from gemm_b200.cc
     syms = subprocess.run(["nm", "-C", "--defined-only", GPU], capture_output=True, text=True, check=True).stdout

@@ -42,6 +42,17 @@ def mlp(cuda, topology, names):
     return R.Net(s, topology[0][0], topology[-1][1])
 
 
+def mlp_component_seam(cuda, topology, names):
+    """The same MLP, the device build out of B200DotProductANNComponent (integration/ann/): its dense
+    forward / backprop / gradients call b200_linear_{fwd,bwd_data,bwd_weight} directly."""
+    s = R.stack()
+    for (i, n, act), (wn, bn) in zip(topology, names):
+        dp = R.b200_dot_product(i, n, wn) if cuda else R.dot_product(i, n, wn)
+        R.push(s, dp, R.bias(n, bn), R.actf(act))
+    R.set_use_cuda(s, cuda)
+    return R.Net(s, topology[0][0], topology[-1][1])
+
+
 def conv(cuda):
     s = R.stack()
     R.push(s, R.rewrap([1, 12, 12]), R.convolution([1, 3, 3], 4, "cw1"), R.convolution_bias(3, 4, "cb1"),
@@ -86,6 +97,9 @@ def main():
         k, v = compare("mlp_digits_bunch%d" % bunch, lambda c: mlp(c, topo, names3), flat,
                        rng.uniform(0, 1, (bunch, 256)).astype(f32), onehot(bunch, 10), rng)
         out[k] = v
+    k, v = compare("mlp_component_seam_bunch32", lambda c: mlp_component_seam(c, topo, names3), flat,
+                   rng.uniform(0, 1, (32, 256)).astype(f32), onehot(32, 10), rng)
+    out[k] = v
     k, v = compare("conv_maxpool", conv, ["cw1", "cb1", "w", "b"],
                    rng.uniform(0, 1, (6, 144)).astype(f32), onehot(6, 5), rng)
     out[k] = v
