@@ -129,6 +129,32 @@ void pick_tile(int M, int N, int K, int sm_count, bool allow_split, bool reduce_
   *split_out = best_split;
 }
 
+
+// Second half of the launch plan, after the tile width and split are chosen (pick_tile or a forced value): split
+// sanity, bytes per ring stage, staging tiles and ring depth.  Pure host arithmetic (also behind b200_debug_tc_plan,
+// which the CPU tests sweep over shapes).
+void finish_plan(TcParams &p, int M, int N, int K, bool b_k, int sms) {
+  if (p.splitk > 2 && !p.reduce_add) p.splitk = 2;
+  {
+    // no empty k slice: every unit must issue at least one MMA (its accumulator is added as it stands)
+    const int nk = (K + BK - 1) / BK;
+    while (p.splitk > 1 && (p.splitk - 1) * ((nk + p.splitk - 1) / p.splitk) >= nk) p.splitk /= 2;
+  }
+  // the ring is as deep as shared memory allows: loads are latency/bandwidth bound, so bytes in flight matter
+  p.stage_bytes = (uint32_t)A_BYTES + (b_k ? (uint32_t)p.BN * BK * 4 : (uint32_t)((p.BN + 31) / 32) * 4096u);
+  {
+    // launches with more tiles than CTAs (persistent CTAs, the epilogue of a tile runs under the next main loop)
+    // fill the device by themselves: they take the whole shared memory and a staging tile per epilogue warp;
+    // single-tile launches stay under SMEM_BUDGET so that light kernels can be resident beside them
+    const long tiles_all = (long)((M + BM - 1) / BM) * ((N + p.BN - 1) / p.BN);
+    const bool multi = p.reduce_add ? tiles_all * p.splitk > sms : (p.splitk != 2 && tiles_all > sms);
+    p.staging_bytes = multi ? (uint32_t)(EPI_WARPS * 4096) : (uint32_t)STAGING_BYTES;
+    const int budget = multi ? SMEM_MAX : SMEM_BUDGET;
+    p.stages = (budget - (SMEM_EXTRA - STAGING_BYTES + (int)p.staging_bytes)) / (int)p.stage_bytes;
+  }
+  if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
+}
+
 }  // namespace
 
 void gemm_tc_destroy(b200_ctx *ctx) {
@@ -158,6 +184,23 @@ extern "C" int b200_debug_tc_override(b200_ctx *ctx, int enable, const uint32_t 
   s->dbg_on = enable != 0;
   if (vals8) memcpy(s->dbg, vals8, sizeof(s->dbg));
   s->force_bn = force_bn;
+  return B200_OK;
+}
+
+// The launch plan of a contraction as pure host logic (no device needed): tile width, k slices, ring depth, whether
+// the launch is planned as persistent multi-tile CTAs, and the grid.  reduce_add = the beta == 1 lean form.
+extern "C" int b200_debug_tc_plan(int M, int N, int K, int b_kmajor, int sm_count, int reduce_add, int *bn, int *splitk,
+                                  int *stages, int *stage_bytes, int *staging_bytes) {
+  if (M <= 0 || N <= 0 || K <= 0 || sm_count <= 0) return B200_ERR_BAD_ARG;
+  TcParams p{};
+  p.reduce_add = reduce_add ? 1 : 0;
+  pick_tile(M, N, K, sm_count, true, reduce_add != 0, &p.BN, &p.splitk);
+  finish_plan(p, M, N, K, b_kmajor != 0, sm_count);
+  if (bn) *bn = p.BN;
+  if (splitk) *splitk = p.splitk;
+  if (stages) *stages = p.stages;
+  if (stage_bytes) *stage_bytes = (int)p.stage_bytes;
+  if (staging_bytes) *staging_bytes = (int)p.staging_bytes;
   return B200_OK;
 }
 
@@ -194,25 +237,7 @@ int gemm_tc(b200_ctx *ctx, int transA, int transB, int M, int N, int K, const fl
     p.BN = s->force_bn & 0xfff;
     p.splitk = (s->force_bn & 0x1000) ? 2 : 1;
   }
-  if (p.splitk > 2 && !p.reduce_add) p.splitk = 2;
-  {
-    // no empty k slice: every unit must issue at least one MMA (its accumulator is added as it stands)
-    const int nk = (K + BK - 1) / BK;
-    while (p.splitk > 1 && (p.splitk - 1) * ((nk + p.splitk - 1) / p.splitk) >= nk) p.splitk /= 2;
-  }
-  // the ring is as deep as shared memory allows: loads are latency/bandwidth bound, so bytes in flight matter
-  p.stage_bytes = (uint32_t)A_BYTES + (b_k ? (uint32_t)p.BN * BK * 4 : (uint32_t)((p.BN + 31) / 32) * 4096u);
-  {
-    // launches with more tiles than CTAs (persistent CTAs, the epilogue of a tile runs under the next main loop)
-    // fill the device by themselves: they take the whole shared memory and a staging tile per epilogue warp;
-    // single-tile launches stay under SMEM_BUDGET so that light kernels can be resident beside them
-    const long tiles_all = (long)((M + BM - 1) / BM) * ((N + p.BN - 1) / p.BN);
-    const bool multi = p.reduce_add ? tiles_all * p.splitk > sms : (p.splitk != 2 && tiles_all > sms);
-    p.staging_bytes = multi ? (uint32_t)(EPI_WARPS * 4096) : (uint32_t)STAGING_BYTES;
-    const int budget = multi ? SMEM_MAX : SMEM_BUDGET;
-    p.stages = (budget - (SMEM_EXTRA - STAGING_BYTES + (int)p.staging_bytes)) / (int)p.stage_bytes;
-  }
-  if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
+  finish_plan(p, M, N, K, b_k, sms);
   if (s->force_stages > 0 && s->force_stages < p.stages) p.stages = s->force_stages;
   p.ldc = ldc;
   p.C = C;
