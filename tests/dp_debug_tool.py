@@ -1,5 +1,5 @@
 """Per-tensor parity of the data-parallel update against the oracle, step by step (GPU box, torchrun).
-    python -m torch.distributed.run --nproc-per-node N tools/dp_debug.py [fp32|tf32] [graph|nograph] [steps]"""
+    python -m torch.distributed.run --nproc-per-node N tests/dp_debug_tool.py [fp32|tf32] [graph|nograph] [steps]"""
 import os
 import sys
 

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Runs the REFERENCE's own components on the GPU through the integration shims.
 
-    APRILREF_LIB=integration/_build/libaprilref_b200.so python tools/ref_on_b200.py
+    APRILREF_LIB=integration/_build/libaprilref_b200.so python tests/ref_on_b200.py
 
 libaprilref_b200.so is the reference's USE_CUDA build (integration/Makefile): its
 Matrix / GPUMirroredMemoryBlock / component / loss code compiled by nvcc for

@@ -48,13 +48,13 @@ def test_shims_are_drop_in_on_the_host_branch():
 
 @pytest.mark.skipif(not (os.path.exists(SHIM) or HAVE_REF), reason="shim build absent and /root/reference absent")
 def test_driver_script_and_component_seam_class_on_the_host_build():
-    """tools/ref_on_b200.py is what the GPU leg runs; on the CPU build set_use_cuda(true) is refused by the
+    """tests/ref_on_b200.py is what the GPU leg runs; on the CPU build set_use_cuda(true) is refused by the
     reference (it stays on the host), so this exercises the script's plumbing and the B200DotProductANNComponent
     class (integration/ann/) on its fall-through to the reference's methods."""
     if not os.path.exists(SHIM):
         _make(SHIM)
     env = dict(os.environ, APRILREF_LIB=SHIM, REF_ON_B200_DRY_RUN="1")
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ref_on_b200.py")], env=env, cwd=ROOT,
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "ref_on_b200.py")], env=env, cwd=ROOT,
                        capture_output=True, text=True, timeout=300)
     line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
     assert r.returncode == 0 and line, r.stdout[-800:] + r.stderr[-800:]
@@ -89,7 +89,7 @@ def test_gpu_build_links_the_reference_to_the_c_abi():
 def test_reference_components_run_on_b200():
     env = dict(os.environ, APRILREF_LIB=GPU)
     try:
-        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ref_on_b200.py")], env=env, cwd=ROOT,
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "ref_on_b200.py")], env=env, cwd=ROOT,
                            capture_output=True, text=True, timeout=300)
     except subprocess.TimeoutExpired:
         pytest.xfail("reference-on-B200 run timed out (first hardware run of this leg)")
