@@ -73,6 +73,11 @@ def lib():
         L.ref_random_free.argtypes = [C.c_void_p]
         L.ref_random_rand.argtypes = [C.c_void_p]
         L.ref_random_randint.argtypes = [C.c_void_p]
+        L.ref_random_rand_n.restype = C.c_double
+        L.ref_random_rand_n.argtypes = [C.c_void_p, C.c_double]
+        L.ref_random_randint_n.restype = C.c_uint
+        L.ref_random_randint_n.argtypes = [C.c_void_p, C.c_uint]
+        L.ref_random_shuffle.argtypes = [C.c_void_p, C.c_int, _I]
         L.ref_gemm.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _F, _F,
                                C.c_float, _F]
         if L.ref_init() != 0:
@@ -300,8 +305,16 @@ class Random:
     def rand(self):
         return lib().ref_random_rand(self.h)
 
-    def randint(self):
-        return lib().ref_random_randint(self.h)
+    def randint(self, n=None):
+        return lib().ref_random_randint(self.h) if n is None else lib().ref_random_randint_n(self.h, n)
+
+    def rand_n(self, n):
+        return lib().ref_random_rand_n(self.h, n)
+
+    def shuffle(self, size):
+        out = (C.c_int * size)()
+        lib().ref_random_shuffle(self.h, size, out)
+        return list(out)
 
 
 def gemm(ta, tb, alpha, a, b, beta, c):

@@ -390,6 +390,10 @@ void* ref_random_new(unsigned int seed) {
 void ref_random_free(void* r) { DecRef(static_cast<Basics::MTRand*>(r)); }
 double ref_random_rand(void* r) { return static_cast<Basics::MTRand*>(r)->rand(); }
 unsigned int ref_random_randint(void* r) { return static_cast<Basics::MTRand*>(r)->randInt(); }
+double ref_random_rand_n(void* r, double n) { return static_cast<Basics::MTRand*>(r)->rand(n); }
+unsigned int ref_random_randint_n(void* r, unsigned int n) { return static_cast<Basics::MTRand*>(r)->randInt(n); }
+// the permutation trainable.supervised_trainer draws for an epoch (0-based here; the Lua binding adds 1)
+void ref_random_shuffle(void* r, int size, int* out) { static_cast<Basics::MTRand*>(r)->shuffle(size, out); }
 
 // ---- raw BLAS-level seam (AprilMath::doGemm through the Matrix API) ------
 
