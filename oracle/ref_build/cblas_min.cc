@@ -13,6 +13,7 @@
 #include <complex>
 #include <cstdio>
 #include <cstdlib>
+#include <vector>
 
 #include "atlas/cblas.h"
 #include "atlas/clapack.h"
@@ -54,19 +55,48 @@ inline T& celem(CBLAS_ORDER order, T* a, int ld, int r, int c) {
   return order == CblasRowMajor ? a[(long)r * ld + c] : a[(long)c * ld + r];
 }
 
+// C = alpha op(A) op(B) + beta C.  A column-major product is the row-major product of the swapped operands
+// (C^T = op(B)^T op(A)^T), so only the row-major case is written out.  Per output row: a dot product over
+// contiguous k when op(B)'s columns are contiguous in k (B transposed), otherwise an axpy of op(B)'s rows into
+// an ACC-typed accumulator row, so that the innermost loop is unit-stride either way.
 template <typename T, typename ACC>
 void gemm(CBLAS_ORDER order, CBLAS_TRANSPOSE ta, CBLAS_TRANSPOSE tb, int m, int n, int k,
           T alpha, const T* a, int lda, const T* b, int ldb, T beta, T* c, int ldc) {
+  if (order != CblasRowMajor) {
+    gemm<T, ACC>(CblasRowMajor, tb, ta, n, m, k, alpha, b, ldb, a, lda, beta, c, ldc);
+    return;
+  }
   const bool at_ = ta != CblasNoTrans, bt_ = tb != CblasNoTrans;
-#pragma omp parallel for schedule(static) if ((long)m * n * k > 1 << 16)
-  for (int i = 0; i < m; ++i)
-    for (int j = 0; j < n; ++j) {
-      ACC s = 0;
-      for (int l = 0; l < k; ++l)
-        s += (ACC)elem(order, at_, a, lda, i, l) * (ACC)elem(order, bt_, b, ldb, l, j);
-      T& out = celem(order, c, ldc, i, j);
-      out = (beta == T(0)) ? alpha * (T)s : alpha * (T)s + beta * out;
+#pragma omp parallel if ((long)m * n * k > 1 << 16)
+  {
+    std::vector<ACC> acc(bt_ ? 0 : n);
+#pragma omp for schedule(static)
+    for (int i = 0; i < m; ++i) {
+      T* crow = c + (long)i * ldc;
+      if (bt_) {
+        for (int j = 0; j < n; ++j) {
+          const T* brow = b + (long)j * ldb;   // op(B)[l, j] = B[j, l]
+          ACC s = 0;
+          if (!at_) {
+            const T* arow = a + (long)i * lda;
+            for (int l = 0; l < k; ++l) s += (ACC)arow[l] * (ACC)brow[l];
+          } else {
+            for (int l = 0; l < k; ++l) s += (ACC)a[(long)l * lda + i] * (ACC)brow[l];
+          }
+          crow[j] = (beta == T(0)) ? alpha * (T)s : alpha * (T)s + beta * crow[j];
+        }
+      } else {
+        for (int j = 0; j < n; ++j) acc[j] = 0;
+        for (int l = 0; l < k; ++l) {
+          const ACC ail = (ACC)(at_ ? a[(long)l * lda + i] : a[(long)i * lda + l]);
+          const T* brow = b + (long)l * ldb;   // op(B)[l, j] = B[l, j]
+          for (int j = 0; j < n; ++j) acc[j] += ail * (ACC)brow[j];
+        }
+        for (int j = 0; j < n; ++j)
+          crow[j] = (beta == T(0)) ? alpha * (T)acc[j] : alpha * (T)acc[j] + beta * crow[j];
+      }
     }
+  }
 }
 
 template <typename T, typename ACC>

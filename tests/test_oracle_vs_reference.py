@@ -320,3 +320,25 @@ def test_gemm_seam(ta, tb):
     want = 0.7 * ((a.T if ta else a).astype(np.float64) @ (b.T if tb else b)) + 0.3 * c
     close(R.gemm(ta, tb, 0.7, a, b, 0.3, c), want)
     close(R.gemm(ta, tb, 1.0, a, b, 0.0, c), (a.T if ta else a).astype(np.float64) @ (b.T if tb else b))
+
+
+# ------------------------------------------------------- BASELINE config C2 at full size
+
+@pytest.mark.parametrize("actf", ["relu", "tanh"])
+def test_c2_full_size_step(actf):
+    """784-2048-2048-10, bunch 1024: the size bench.py's parity object checks the GPU at.  The oracle used there
+    agrees with the reference's own classes on the whole step (a few seconds of host time per side)."""
+    rng = np.random.default_rng(77)
+    net, o, names = mlp_pair([(784, 2048, actf), (2048, 2048, actf), (2048, 10, "log_softmax")],
+                             [("w1", "b1"), ("w2", "b2"), ("w3", "b3")], rng)
+    # weights of the bench's scale: uniform(+-1/sqrt(fan_in + fan_out))
+    ow = o.components[0].w          # the oracle's weights dictionary (shared by all of its components)
+    for n in names:
+        shape = net.weight(n).shape
+        a = 1.0 / np.sqrt(sum(shape)) if shape[1] > 1 else 1.0 / np.sqrt(shape[0])
+        w = rng.uniform(-a, a, shape).astype(f32)
+        net.set_weight(n, w)
+        ow[n][...] = w
+    x = rng.uniform(-1, 1, (1024, 784)).astype(f32)
+    check_step(net, o, names, x, one_hot(rng, 1024, 10), "multi_class_cross_entropy", A.MultiClassCrossEntropy(), 4e-6)
+    net.close()
