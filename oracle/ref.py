@@ -235,11 +235,11 @@ class Net:
     def shared_count(self, name):
         return lib().ref_net_shared_count(self.h, _b(name))
 
-    def _run(self, fn, x, *extra):
+    def _run(self, fn, x, *extra, out_elems=None):
         x = _f32(x)
         nd = C.c_int(0)
         dims = (C.c_int * 8)()
-        cap = 1 << 24
+        cap = int(out_elems) if out_elems else 1 << 24
         out = np.empty(cap, np.float32)
         n = fn(self.h, _fp(x), x.ndim, _ints(x.shape), *extra, _fp(out), cap, C.byref(nd), dims)
         if n == REF_FAILED:
@@ -250,11 +250,12 @@ class Net:
             return None
         return out[:n].reshape([dims[i] for i in range(nd.value)]).copy()
 
-    def forward(self, x, during_training=False):
-        return self._run(lib().ref_net_forward, x, int(during_training))
+    def forward(self, x, during_training=False, out_elems=None):
+        """out_elems: size of the marshalling buffer when the output exceeds 16 Mi floats"""
+        return self._run(lib().ref_net_forward, x, int(during_training), out_elems=out_elems)
 
-    def backprop(self, e):
-        return self._run(lib().ref_net_backprop, e)
+    def backprop(self, e, out_elems=None):
+        return self._run(lib().ref_net_backprop, e, out_elems=out_elems)
 
     def compute_gradients(self):
         if lib().ref_net_compute_gradients(self.h) == REF_FAILED:

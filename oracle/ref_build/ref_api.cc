@@ -98,6 +98,10 @@ const char* opt_name(const char* s) { return (s && *s) ? s : 0; }
 
 MatrixFloat* matrix_from(const float* data, int ndims, const int* dims) {
   MatrixFloat* m = new MatrixFloat(ndims, dims);
+  if (m->getIsContiguous()) {   // a fresh matrix is row-major and dense: one block copy
+    std::memcpy(m->getRawDataAccess()->getPPALForWrite() + m->getOffset(), data, sizeof(float) * (size_t)m->size());
+    return m;
+  }
   const float* p = data;
   for (MatrixFloat::iterator it(m->begin()); it != m->end(); ++it) *it = *p++;
   return m;
@@ -111,8 +115,12 @@ int matrix_to(const MatrixFloat* m, float* out, int cap, int* ndims_out, int* di
     for (int i = 0; i < m->getNumDim(); ++i) dims_out[i] = m->getDimSize(i);
   if (out) {
     if (m->size() > cap) return -m->size();
-    float* p = out;
-    for (MatrixFloat::const_iterator it(m->begin()); it != m->end(); ++it) *p++ = *it;
+    if (m->getIsContiguous()) {
+      std::memcpy(out, m->getRawDataAccess()->getPPALForRead() + m->getOffset(), sizeof(float) * (size_t)m->size());
+    } else {
+      float* p = out;
+      for (MatrixFloat::const_iterator it(m->begin()); it != m->end(); ++it) *p++ = *it;
+    }
   }
   return m->size();
 }

@@ -1,16 +1,16 @@
-"""BASELINE config C2 at FULL SIZE (784-2048-2048-10, bunch 1024), CUDA path against THE REFERENCE ITSELF:
-the reference's own HyperplaneANNComponent / ActivationFunctionANNComponent / MultiClassCrossEntropyLossFunction
+"""BASELINE configs at FULL SIZE, CUDA path against THE REFERENCE ITSELF: the reference's own component and loss
 objects (oracle/_ref/libaprilref.so, compiled in place from the reference's sources; it travels to the GPU box
 as a prebuilt library) run the same weights and bunch on the host cores, and the product's results are held to
 them with no numpy restatement in between.
 
-  * ReLU network (the bench's): forward log-probabilities and per-row losses.  (Gradients of a ReLU net at this
-    size are compared gate-aware in test_gpu_fullsize.py: one unit within rounding of zero flips.)
-  * tanh network of the same shapes: forward, losses and every smoothed weight / bias gradient.
+  C2      784-2048-2048-10 ReLU, bunch 1024 (the bench's): forward log-probabilities and per-row losses
+  C2tanh  the same shapes with tanh: forward, losses and every smoothed weight / bias gradient
+  C4      the convolution / max-pooling net on 1x28x28, bunch 512: forward and losses
+  C5      512 -> 10 000 log_softmax, bunch 4096: forward, losses and both gradients
 
-fp32 (FFMA) mode; tolerance 1e-4 of each tensor's largest magnitude (fp32 accumulation over K = 2048 on the
-device, double accumulation in the reference build's plain-loop BLAS)."""
-import math
+(Gradients of the ReLU / max-pool networks at these sizes are compared gate-aware in test_gpu_fullsize.py: a unit
+within rounding of zero flips its gate.)  fp32 (FFMA) mode; tolerance 1e-4 of each tensor's largest magnitude
+(fp32 accumulation on the device, double accumulation in the reference build's plain-loop BLAS)."""
 import os
 import sys
 
@@ -19,14 +19,15 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
 
 from oracle import ref as R  # noqa: E402
+from reference_configs import NAMES, SHAPES, inputs, reference_step  # noqa: E402
 
 pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(not R.available(), reason="oracle/_ref/libaprilref.so not present")]
 
-BUNCH, TOL = 1024, 1e-4
-NAMES = ["w1", "b1", "w2", "b2", "w3", "b3"]
+TOL = 1e-4
 
 
 @pytest.fixture(scope="module")
@@ -42,37 +43,14 @@ def rel_err(a, b):
     return float(np.abs(a - b).max() / max(1.0, np.abs(b).max()))
 
 
-def reference_net(actf):
-    s = R.stack()
-    R.push(s, R.hyperplane(784, 2048, "w1", "b1"), R.actf(actf), R.hyperplane(2048, 2048, "w2", "b2"), R.actf(actf),
-           R.hyperplane(2048, 10, "w3", "b3"), R.actf("log_softmax"))
-    return R.Net(s, 784, 10)
-
-
-def reference_step(net, weights, x, t):
-    """forward, per-row MCCE, backward and raw gradients out of the reference's own classes"""
-    for n in NAMES:
-        net.set_weight(n, weights[n])
-    y = net.forward(x, True)
-    loss = R.Loss("multi_class_cross_entropy", 10)
-    rows = loss.loss_rows(y, t)
-    net.backprop(loss.gradient(y, t))
-    net.compute_gradients()
-    return y, rows, {n: net.gradient(n) for n in NAMES}, {n: net.shared_count(n) for n in NAMES}
-
-
-def inputs():
-    rs = np.random.RandomState(2026)
-    x = rs.uniform(-1, 1, size=(BUNCH, 784)).astype(np.float32)
-    t = np.zeros((BUNCH, 10), np.float32)
-    t[np.arange(BUNCH), rs.randint(0, 10, size=BUNCH)] = 1.0
-    return x, t
-
-
-def product_trainer(ann, actf):
-    topo = "784 inputs 2048 %s 2048 %s 10 log_softmax" % (actf, actf)
-    tr = ann.trainable.supervised_trainer(ann.mlp.all_all.generate(topo), ann.loss.multi_class_cross_entropy(),
-                                          BUNCH).build()
+def product_trainer(ann, name):
+    from april_ann_b200 import configs
+    bunch, nin, nout = SHAPES[name]
+    if name == "C2tanh":
+        tr = ann.trainable.supervised_trainer(ann.mlp.all_all.generate("784 inputs 2048 tanh 2048 tanh 10 log_softmax"),
+                                              ann.loss.multi_class_cross_entropy(), bunch).build()
+    else:
+        tr = configs.build_trainer(ann, name)
     tr.set_option("learning_rate", 0.01)
     tr.set_option("momentum", 0.0)
     tr.set_option("weight_decay", 0.0)
@@ -81,21 +59,18 @@ def product_trainer(ann, actf):
     return tr
 
 
-@pytest.mark.parametrize("actf", ["relu", "tanh"])
-def test_c2_full_size_against_the_reference(ann, actf):
-    tr = product_trainer(ann, actf)
-    assert sorted(tr.weight_names()) == sorted(NAMES)
-    weights = {n: tr.weights(n) for n in NAMES}
-    x, t = inputs()
-    net = reference_net(actf)
-    y_ref, rows_ref, g_ref, counts = reference_step(net, weights, x, t)
-    net.close()
+@pytest.mark.parametrize("name,with_gradients", [("C2", False), ("C2tanh", True), ("C4", False), ("C5", True)])
+def test_full_size_against_the_reference(ann, name, with_gradients):
+    tr = product_trainer(ann, name)
+    assert sorted(tr.weight_names()) == sorted(NAMES[name])
+    weights = {n: tr.weights(n) for n in NAMES[name]}
+    x, t = inputs(name)
+    y_ref, rows_ref, g_ref, scale = reference_step(R, name, weights, x, t)
 
     assert rel_err(tr.calculate(x), y_ref) <= TOL
     mean, rows = tr.train_step(x, t)
     assert rel_err(rows, rows_ref) <= TOL
     assert abs(mean - float(rows_ref.mean())) <= TOL * max(1.0, float(rows_ref.mean()))
-    if actf == "tanh":
-        for n in NAMES:
-            scale = 1.0 / math.sqrt(max(counts[n], 1) * BUNCH)      # supervised.lua:797-803
-            assert rel_err(tr.gradients(n), g_ref[n].astype(np.float64) * scale) <= TOL, n
+    if with_gradients:
+        for n in NAMES[name]:
+            assert rel_err(tr.gradients(n), g_ref[n].astype(np.float64) * scale[n]) <= TOL, n
