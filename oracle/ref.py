@@ -135,8 +135,10 @@ def stack():
 
 
 def push(s, *comps):
+    """The stack takes its own reference on each component; the constructor's is released here."""
     for c in comps:
         lib().ref_stack_push(s, c)
+        lib().ref_component_free(c)
     return s
 
 
@@ -205,6 +207,7 @@ class Net:
         self.h = lib().ref_net_build(root, input_size, output_size)
         if not self.h:
             _raise()
+        lib().ref_component_free(root)      # the net holds its own reference on the root
 
     def close(self):
         if self.h:
