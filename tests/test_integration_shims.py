@@ -90,7 +90,7 @@ def test_reference_components_run_on_b200():
     env = dict(os.environ, APRILREF_LIB=GPU)
     try:
         r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "ref_on_b200.py")], env=env, cwd=ROOT,
-                           capture_output=True, text=True, timeout=300)
+                           capture_output=True, text=True, timeout=120)
     except subprocess.TimeoutExpired:
         pytest.xfail("reference-on-B200 run timed out (first hardware run of this leg)")
     line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
